@@ -1,0 +1,690 @@
+"""Python side of the drop-in boundary: ctypes bindings of ``librefiners_b200.so`` (the C ABI
+declared in include/refiners_b200.h) surfaced as ``torch.ops.refiners_b200.*`` custom ops.
+
+Rules enforced here:
+  * CUDA tensors only ever run on our kernels.  If the shared library is missing the first
+    call raises - there is no ATen/CPU fallback behind these ops.
+  * Inference only: ops refuse to run when autograd would need a graph.
+  * Nothing here synchronises or allocates outside torch's caching allocator, so every op is
+    CUDA-graph capturable.
+  * Packed weights (conv KRSC layout, GEGLU interleave, concatenated LoRA factors) are cached
+    per parameter storage + version, as the reference swaps ``.weight`` objects freely
+    (fluxion/adapters/lora.py:168-178, image_prompt.py:344-347 in the reference).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+from typing import Any, Sequence
+
+import torch
+from torch import Tensor
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / "csrc" / "librefiners_b200.so"
+_lib: ctypes.CDLL | None = None
+_DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+_UNARY = {"silu": 0, "gelu": 1, "gelu_tanh": 2, "gelu_sigmoid": 3, "relu": 4, "sigmoid": 5}
+EPI_NONE, EPI_GEGLU, EPI_GELU, EPI_SILU = 0, 1, 2, 3
+
+_fusion = os.environ.get("RB200_FUSION", "1") != "0"
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def fusion_enabled() -> bool:
+    return _fusion
+
+
+def set_fusion(enabled: bool) -> bool:
+    global _fusion
+    previous, _fusion = _fusion, bool(enabled)
+    return previous
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def is_built() -> bool:
+    return _LIB_PATH.exists()
+
+
+class _LoraDesc(ctypes.Structure):
+    _fields_ = [("down", ctypes.c_void_p), ("up", ctypes.c_void_p), ("scale", ctypes.c_float), ("rank", ctypes.c_int32)]
+
+
+_P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
+    "rb200_abi_version": (_I, []),
+    "rb200_last_error": (ctypes.c_char_p, []),
+    "rb200_device_info": (_I, [ctypes.POINTER(_I)] * 3),
+    "rb200_launch_count": (_L, []),
+    "rb200_set_kernel_mode": (_I, [_I]),
+    "rb200_linear_workspace_bytes": (_Z, [_L, _I, _I]),
+    "rb200_linear": (_I, [_P, _I, _P, _L, _P, _L, _P, _P, _L, _L, _L, _L, _I, _P, _P, _P, _P, _L, _I, _P, _Z]),
+    "rb200_lora_pack": (_I, [_P, _I, _I, ctypes.POINTER(_LoraDesc), _L, _L, _P, _P, _P, _I]),
+    "rb200_geglu_pack": (_I, [_P, _I, _P, _P, _P, _P, _L, _L]),
+    "rb200_conv2d_pack_weight": (_I, [_P, _I, _P, _P, _L, _L, _I, _I]),
+    "rb200_conv2d": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I]),
+    "rb200_group_norm_workspace_bytes": (_Z, [_L, _L, _L]),
+    "rb200_group_norm": (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _F, _P, _P, _I, _P, _Z]),
+    "rb200_layer_norm": (_I, [_P, _I, _P, _P, _L, _L, _F, _P, _P]),
+    "rb200_unary": (_I, [_P, _I, _P, _P, _L, _I]),
+    "rb200_geglu": (_I, [_P, _I, _P, _P, _L, _L]),
+    "rb200_add": (_I, [_P, _I, _P, _P, _P, _L, _F]),
+    "rb200_sdpa": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _L, _L, _I] + [_L] * 8 + [_F, _I, _P, _P, _L] + [_L] * 4 + [_F]),
+    "rb200_sam_attention_workspace_bytes": (_Z, [_L, _I, _I, _I, _I]),
+    "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
+}
+
+
+def exported_symbols() -> list[str]:
+    return list(_SIGNATURES)
+
+
+def load_library() -> ctypes.CDLL:
+    """Load (once) and type the C ABI.  Raises BackendError when the .so is absent or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise BackendError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  refiners_b200 has no fallback for CUDA tensors."
+        )
+    lib = ctypes.CDLL(str(_LIB_PATH))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the header and the .so disagree
+        fn.restype, fn.argtypes = restype, argtypes
+    if lib.rb200_abi_version() != 1:
+        raise BackendError(f"ABI mismatch: library reports {lib.rb200_abi_version()}, bindings expect 1")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        message = load_library().rb200_last_error()
+        raise BackendError(f"rb200 error {rc}: {message.decode() if message else '?'}")
+
+
+def launch_count() -> int:
+    return int(load_library().rb200_launch_count())
+
+
+def set_kernel_mode(mode: int) -> int:
+    return int(load_library().rb200_set_kernel_mode(int(mode)))
+
+
+def device_info() -> tuple[int, int, int]:
+    a, b, c = _I(), _I(), _I()
+    _check(load_library().rb200_device_info(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _dtype_code(t: Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise BackendError(f"unsupported dtype {t.dtype} (bf16, fp16, fp32 only)") from None
+
+
+def _inference_only(*tensors: Tensor | None) -> None:
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise BackendError(
+            "refiners_b200 kernels are inference-only: wrap the call in refiners_b200.fluxion.no_grad() "
+            "(training through the custom ops is out of scope)"
+        )
+
+
+def _same(x: Tensor, *others: Tensor | None) -> None:
+    for o in others:
+        if o is not None and (o.dtype != x.dtype or o.device != x.device):
+            raise BackendError(f"operand mismatch: {o.dtype}@{o.device} vs {x.dtype}@{x.device}")
+
+
+# ------------------------------------------------------------------------------------ caches
+class _PackCache:
+    """Derived tensors keyed on the identity of their sources (storage pointer, version, shape)."""
+
+    def __init__(self, limit: int = 8192) -> None:
+        self._items: dict[tuple[Any, ...], Tensor | tuple[Tensor, ...]] = {}
+        self._limit = limit
+
+    @staticmethod
+    def key(*tensors: Tensor | None) -> tuple[Any, ...]:
+        return tuple(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in tensors)
+
+    def get(self, key: tuple[Any, ...]) -> Any:
+        return self._items.get(key)
+
+    def put(self, key: tuple[Any, ...], value: Any) -> Any:
+        if len(self._items) >= self._limit:
+            self._items.clear()
+        self._items[key] = value
+        return value
+
+    def clear(self) -> None:
+        self._items.clear()
+
+
+_conv_cache = _PackCache()
+_geglu_cache = _PackCache()
+_lora_cache = _PackCache()
+
+
+def clear_caches() -> None:
+    _conv_cache.clear()
+    _geglu_cache.clear()
+    _lora_cache.clear()
+
+
+# ------------------------------------------------------------------------- raw op kernels
+def _linear_impl(
+    x: Tensor,
+    w: Tensor,
+    bias: Tensor | None,
+    residual: Tensor | None,
+    lora_down: Tensor | None,
+    lora_up: Tensor | None,
+    lora_scale: Tensor | None,
+    epilogue: int,
+) -> Tensor:
+    lib = load_library()
+    _same(x, w, bias, residual, lora_down, lora_up)
+    K = x.shape[-1]
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise BackendError(f"linear: x[..., {K}] incompatible with weight {tuple(w.shape)}")
+    x2 = x.reshape(-1, K)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    M = x2.shape[0]
+    n_out = N // 2 if epilogue == EPI_GEGLU else N
+    y = torch.empty((M, n_out), device=x.device, dtype=x.dtype)
+    res2 = None
+    if residual is not None:
+        res2 = residual.reshape(-1, n_out)
+        if res2.stride(-1) != 1:
+            res2 = res2.contiguous()
+        if res2.shape[0] != M:
+            raise BackendError("linear: residual shape mismatch")
+    r_pad = 0 if lora_down is None else lora_down.shape[0]
+    ws = None
+    ws_bytes = 0
+    if r_pad:
+        ws_bytes = lib.rb200_linear_workspace_bytes(M, r_pad, _dtype_code(x))
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    if M > 0:
+        _check(
+            lib.rb200_linear(
+                _stream(), _dtype_code(x), x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), _ptr(bias),
+                y.data_ptr(), y.stride(0), M, N, K, r_pad, _ptr(lora_down), _ptr(lora_up), _ptr(lora_scale),
+                _ptr(res2), 0 if res2 is None else res2.stride(0), epilogue, _ptr(ws), ws_bytes,
+            )
+        )
+    return y.reshape(*x.shape[:-1], n_out)
+
+
+def _conv2d_impl(
+    x: Tensor,
+    w_packed: Tensor,
+    bias: Tensor | None,
+    chan_bias: Tensor | None,
+    residual: Tensor | None,
+    R: int,
+    S: int,
+    stride: int,
+    pad: int,
+    epilogue: int,
+) -> Tensor:
+    lib = load_library()
+    _same(x, w_packed, bias, chan_bias, residual)
+    B, Cin, H, W = x.shape
+    taps, Cout, cin_w = w_packed.shape
+    if taps != R * S or cin_w != Cin:
+        raise BackendError(f"conv2d: input {tuple(x.shape)} incompatible with packed weight {tuple(w_packed.shape)}")
+    Ho = (H + 2 * pad - R) // stride + 1
+    Wo = (W + 2 * pad - S) // stride + 1
+    xc = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, Cout, Ho, Wo), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if residual is not None:
+        if residual.shape != y.shape:
+            raise BackendError("conv2d: residual shape mismatch")
+        residual = residual.contiguous(memory_format=torch.channels_last)
+    if chan_bias is not None:
+        chan_bias = chan_bias.reshape(B, Cout).contiguous()
+    if y.numel():
+        _check(
+            lib.rb200_conv2d(
+                _stream(), _dtype_code(x), xc.data_ptr(), w_packed.data_ptr(), _ptr(bias), _ptr(chan_bias),
+                _ptr(residual), y.data_ptr(), B, H, W, Cin, Cout, R, S, stride, pad, epilogue,
+            )
+        )
+    return y
+
+
+def _group_norm_impl(x: Tensor, groups: int, gamma: Tensor, beta: Tensor, eps: float, silu: bool) -> Tensor:
+    lib = load_library()
+    _same(x, gamma, beta)
+    if x.ndim < 3:
+        raise BackendError("group_norm expects [B, C, *spatial]")
+    B, C = x.shape[0], x.shape[1]
+    if x.ndim == 4:
+        xc = x.contiguous(memory_format=torch.channels_last)
+        y = torch.empty_like(xc, memory_format=torch.channels_last)
+        HW = x.shape[2] * x.shape[3]
+        xk, yk = xc, y
+    else:  # [B, C, L]: normalise a channels-last copy, hand back the original layout
+        xk = x.flatten(2).transpose(1, 2).contiguous()
+        yk = torch.empty_like(xk)
+        HW = xk.shape[1]
+        y = None
+    ws_bytes = lib.rb200_group_norm_workspace_bytes(B, HW, C)
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    if xk.numel():
+        _check(
+            lib.rb200_group_norm(
+                _stream(), _dtype_code(x), xk.data_ptr(), yk.data_ptr(), B, HW, C, groups, float(eps),
+                gamma.data_ptr(), beta.data_ptr(), int(silu), ws.data_ptr(), ws_bytes,
+            )
+        )
+    if y is None:
+        return yk.transpose(1, 2).reshape(x.shape)
+    return y
+
+
+def _layer_norm_impl(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    lib = load_library()
+    _same(x, gamma, beta)
+    C = x.shape[-1]
+    xc = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty_like(xc)
+    rows = xc.numel() // C if C else 0
+    if rows:
+        _check(
+            lib.rb200_layer_norm(
+                _stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), rows, C, float(eps), gamma.data_ptr(),
+                beta.data_ptr(),
+            )
+        )
+    return y
+
+
+def _dense_like(x: Tensor) -> Tensor:
+    """x itself when its memory is a dense permutation (contiguous or channels-last), else a copy."""
+    if x.is_contiguous() or (x.ndim == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        return x
+    return x.contiguous()
+
+
+def _unary_impl(x: Tensor, op: int) -> Tensor:
+    lib = load_library()
+    xc = _dense_like(x)
+    y = torch.empty_like(xc)
+    if xc.numel():
+        _check(lib.rb200_unary(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), xc.numel(), op))
+    return y
+
+
+def _geglu_impl(x: Tensor) -> Tensor:
+    lib = load_library()
+    F2 = x.shape[-1]
+    xc = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty((*x.shape[:-1], F2 // 2), device=x.device, dtype=x.dtype)
+    rows = xc.numel() // F2 if F2 else 0
+    if rows:
+        _check(lib.rb200_geglu(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), rows, F2 // 2))
+    return y
+
+
+def _add_impl(a: Tensor, b: Tensor, alpha: float) -> Tensor:
+    lib = load_library()
+    _same(a, b)
+    if a.shape != b.shape:
+        raise BackendError("add: shapes differ (broadcasting stays in ATen)")
+    ac = _dense_like(a)
+    if b.stride() != ac.stride():
+        b = b.contiguous(memory_format=torch.channels_last) if (
+            ac.ndim == 4 and not ac.is_contiguous()
+        ) else b.contiguous()
+        if b.stride() != ac.stride():
+            ac = ac.contiguous()
+            b = b.contiguous()
+    y = torch.empty_like(ac)
+    if ac.numel():
+        _check(lib.rb200_add(_stream(), _dtype_code(a), ac.data_ptr(), b.data_ptr(), y.data_ptr(), ac.numel(), alpha))
+    return y
+
+
+def _rows(t: Tensor) -> Tensor:
+    """[B, S, C] view with unit channel stride (copy only if needed)."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _sdpa_impl(
+    q: Tensor, k: Tensor, v: Tensor, k2: Tensor | None, v2: Tensor | None, heads: int, causal: bool, scale2: float
+) -> Tensor:
+    lib = load_library()
+    _same(q, k, v, k2, v2)
+    B, Sq, C = q.shape
+    Sk = k.shape[1]
+    if C % heads or k.shape[2] != C or v.shape[2] != C or k.shape[0] != B or v.shape[0] != B or v.shape[1] != Sk:
+        raise BackendError(f"sdpa: bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)} heads={heads}")
+    D = C // heads
+    q, k, v = _rows(q), _rows(k), _rows(v)
+    o = torch.empty((B, Sq, C), device=q.device, dtype=q.dtype)
+    Sk2 = 0
+    if k2 is not None:
+        assert v2 is not None
+        k2, v2 = _rows(k2), _rows(v2)
+        Sk2 = k2.shape[1]
+    if o.numel():
+        _check(
+            lib.rb200_sdpa(
+                _stream(), _dtype_code(q), q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), B, heads, Sq, Sk, D,
+                q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), o.stride(0), o.stride(1),
+                float(D) ** -0.5, int(causal), _ptr(k2), _ptr(v2), Sk2,
+                0 if k2 is None else k2.stride(0), 0 if k2 is None else k2.stride(1),
+                0 if v2 is None else v2.stride(0), 0 if v2 is None else v2.stride(1), float(scale2),
+            )
+        )
+    return o
+
+
+def _sam_attention_impl(qkv: Tensor, rel_h: Tensor, rel_w: Tensor, heads: int) -> Tensor:
+    lib = load_library()
+    _same(qkv, rel_h, rel_w)
+    Bw, Hh, Ww, C3 = qkv.shape
+    C = C3 // 3
+    d = C // heads
+    qc = qkv if qkv.is_contiguous() else qkv.contiguous()
+    o = torch.empty((Bw, Hh, Ww, C), device=qkv.device, dtype=qkv.dtype)
+    ws_bytes = lib.rb200_sam_attention_workspace_bytes(Bw, Hh, Ww, heads, d)
+    ws = torch.empty(ws_bytes, device=qkv.device, dtype=torch.uint8)
+    if o.numel():
+        _check(
+            lib.rb200_sam_attention(
+                _stream(), _dtype_code(qkv), qc.data_ptr(), rel_h.contiguous().data_ptr(),
+                rel_w.contiguous().data_ptr(), o.data_ptr(), Bw, Hh, Ww, heads, d, ws.data_ptr(), ws_bytes,
+            )
+        )
+    return o
+
+
+# --------------------------------------------------------------- torch custom-op registration
+_torch_lib = torch.library.Library("refiners_b200", "DEF")
+_torch_lib.define(
+    "linear(Tensor x, Tensor w, Tensor? bias, Tensor? residual, Tensor? lora_down, Tensor? lora_up, "
+    "Tensor? lora_scale, int epilogue) -> Tensor"
+)
+_torch_lib.define(
+    "conv2d(Tensor x, Tensor w_packed, Tensor? bias, Tensor? chan_bias, Tensor? residual, int R, int S, "
+    "int stride, int pad, int epilogue) -> Tensor"
+)
+_torch_lib.define("group_norm(Tensor x, int groups, Tensor gamma, Tensor beta, float eps, bool silu) -> Tensor")
+_torch_lib.define("layer_norm(Tensor x, Tensor gamma, Tensor beta, float eps) -> Tensor")
+_torch_lib.define("unary(Tensor x, int op) -> Tensor")
+_torch_lib.define("geglu(Tensor x) -> Tensor")
+_torch_lib.define("add(Tensor a, Tensor b, float alpha) -> Tensor")
+_torch_lib.define(
+    "sdpa(Tensor q, Tensor k, Tensor v, Tensor? k2, Tensor? v2, int heads, bool causal, float scale2) -> Tensor"
+)
+_torch_lib.define("sam_attention(Tensor qkv, Tensor rel_h, Tensor rel_w, int heads) -> Tensor")
+
+for _name, _fn in (
+    ("linear", _linear_impl),
+    ("conv2d", _conv2d_impl),
+    ("group_norm", _group_norm_impl),
+    ("layer_norm", _layer_norm_impl),
+    ("unary", _unary_impl),
+    ("geglu", _geglu_impl),
+    ("add", _add_impl),
+    ("sdpa", _sdpa_impl),
+    ("sam_attention", _sam_attention_impl),
+):
+    _torch_lib.impl(_name, _fn, "CUDA")
+
+
+@torch.library.register_fake("refiners_b200::linear")
+def _linear_fake(x, w, bias, residual, lora_down, lora_up, lora_scale, epilogue):  # type: ignore[no-untyped-def]
+    n = w.shape[0] // 2 if epilogue == EPI_GEGLU else w.shape[0]
+    return x.new_empty((*x.shape[:-1], n))
+
+
+@torch.library.register_fake("refiners_b200::conv2d")
+def _conv2d_fake(x, w_packed, bias, chan_bias, residual, R, S, stride, pad, epilogue):  # type: ignore[no-untyped-def]
+    B, _, H, W = x.shape
+    return x.new_empty((B, w_packed.shape[1], (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1))
+
+
+@torch.library.register_fake("refiners_b200::group_norm")
+def _group_norm_fake(x, groups, gamma, beta, eps, silu):  # type: ignore[no-untyped-def]
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("refiners_b200::layer_norm")
+def _layer_norm_fake(x, gamma, beta, eps):  # type: ignore[no-untyped-def]
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("refiners_b200::unary")
+def _unary_fake(x, op):  # type: ignore[no-untyped-def]
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("refiners_b200::geglu")
+def _geglu_fake(x):  # type: ignore[no-untyped-def]
+    return x.new_empty((*x.shape[:-1], x.shape[-1] // 2))
+
+
+@torch.library.register_fake("refiners_b200::add")
+def _add_fake(a, b, alpha):  # type: ignore[no-untyped-def]
+    return torch.empty_like(a)
+
+
+@torch.library.register_fake("refiners_b200::sdpa")
+def _sdpa_fake(q, k, v, k2, v2, heads, causal, scale2):  # type: ignore[no-untyped-def]
+    return torch.empty_like(q)
+
+
+@torch.library.register_fake("refiners_b200::sam_attention")
+def _sam_attention_fake(qkv, rel_h, rel_w, heads):  # type: ignore[no-untyped-def]
+    return qkv.new_empty((*qkv.shape[:-1], qkv.shape[-1] // 3))
+
+
+_ops = torch.ops.refiners_b200
+
+
+# ----------------------------------------------------------------------------- public helpers
+def pack_loras(x: Tensor, w: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> tuple[Tensor, Tensor, Tensor]:
+    """(down_cat[r_pad, K], up_cat[N, r_pad], colscale[r_pad]) for rb200_linear, cached."""
+    key = _PackCache.key(*[t for d, u, _ in loras for t in (d, u)]) + tuple(s for _, _, s in loras)
+    hit = _lora_cache.get(key)
+    if hit is not None:
+        return hit
+    lib = load_library()
+    N, K = w.shape
+    total = sum(d.shape[0] for d, _, _ in loras)
+    r_pad = (total + 63) // 64 * 64
+    descs = (_LoraDesc * len(loras))()
+    keep = []
+    for i, (d, u, s) in enumerate(loras):
+        d, u = d.contiguous(), u.contiguous()
+        keep += [d, u]
+        if d.shape[1] != K or u.shape[0] != N or u.shape[1] != d.shape[0]:
+            raise BackendError(f"LoRA {i}: down{tuple(d.shape)} / up{tuple(u.shape)} do not fit Linear({K}->{N})")
+        _same(w, d, u)
+        descs[i] = _LoraDesc(d.data_ptr(), u.data_ptr(), float(s), d.shape[0])
+    down_cat = torch.empty((r_pad, K), device=w.device, dtype=w.dtype)
+    up_cat = torch.empty((N, r_pad), device=w.device, dtype=w.dtype)
+    colscale = torch.empty((r_pad,), device=w.device, dtype=torch.float32)
+    _check(
+        lib.rb200_lora_pack(
+            _stream(), _dtype_code(w), len(loras), descs, N, K, down_cat.data_ptr(), up_cat.data_ptr(),
+            colscale.data_ptr(), r_pad,
+        )
+    )
+    return _lora_cache.put(key, (down_cat, up_cat, colscale))
+
+
+def lora_fusable(x: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> bool:
+    return len(loras) > 0 and all(d.is_cuda and u.is_cuda and d.dtype == x.dtype for d, u, _ in loras)
+
+
+def linear(
+    x: Tensor,
+    weight: Tensor,
+    bias: Tensor | None = None,
+    *,
+    residual: Tensor | None = None,
+    loras: Sequence[tuple[Tensor, Tensor, float]] = (),
+    epilogue: int = EPI_NONE,
+) -> Tensor:
+    _inference_only(x, weight, bias)
+    down = up = scale = None
+    if loras:
+        down, up, scale = pack_loras(x, weight, loras)
+    return _ops.linear(x, weight, bias, residual, down, up, scale, epilogue)
+
+
+def linear_geglu(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
+    """``GLU(GeLU)(Linear(x))`` in one launch; the value/gate interleave of W is cached."""
+    _inference_only(x, weight, bias)
+    key = _PackCache.key(weight, bias)
+    packed = _geglu_cache.get(key)
+    if packed is None:
+        lib = load_library()
+        w = weight.contiguous()
+        wp = torch.empty_like(w)
+        bp = None if bias is None else torch.empty_like(bias)
+        _check(
+            lib.rb200_geglu_pack(
+                _stream(), _dtype_code(w), w.data_ptr(), _ptr(bias), wp.data_ptr(), _ptr(bp), w.shape[0] // 2, w.shape[1]
+            )
+        )
+        packed = _geglu_cache.put(key, (wp, bp))
+    wp, bp = packed
+    return _ops.linear(x, wp, bp, None, None, None, None, EPI_GEGLU)
+
+
+def geglu_fusable(weight: Tensor) -> bool:
+    return weight.dtype in (torch.bfloat16, torch.float16) and (weight.shape[0] // 2) % 16 == 0 and weight.shape[1] % 8 == 0
+
+
+def packed_conv_weight(weight: Tensor) -> Tensor:
+    key = _PackCache.key(weight)
+    packed = _conv_cache.get(key)
+    if packed is None:
+        lib = load_library()
+        w = weight.contiguous()
+        Cout, Cin, R, S = w.shape
+        packed = torch.empty((R * S, Cout, Cin), device=w.device, dtype=w.dtype)
+        _check(lib.rb200_conv2d_pack_weight(_stream(), _dtype_code(w), w.data_ptr(), packed.data_ptr(), Cout, Cin, R, S))
+        _conv_cache.put(key, packed)
+    return packed
+
+
+def conv2d(
+    x: Tensor,
+    weight: Tensor,
+    bias: Tensor | None,
+    stride: int,
+    padding: int,
+    *,
+    chan_bias: Tensor | None = None,
+    residual: Tensor | None = None,
+    epilogue: int = EPI_NONE,
+) -> Tensor:
+    _inference_only(x, weight, bias)
+    R, S = weight.shape[2], weight.shape[3]
+    return _ops.conv2d(x, packed_conv_weight(weight), bias, chan_bias, residual, R, S, stride, padding, epilogue)
+
+
+def conv_supported(module: Any) -> bool:
+    s, p, d = module.stride, module.padding, module.dilation
+    return (
+        module.groups == 1
+        and module.padding_mode == "zeros"
+        and not isinstance(p, str)
+        and s[0] == s[1]
+        and p[0] == p[1]
+        and tuple(d) == (1, 1)
+    )
+
+
+def conv2d_module(x: Tensor, module: Any, **fused: Any) -> Tensor:
+    """Run a fluxion ``Conv2d`` leaf.  Unsupported conv flavours (groups, dilation, string or
+    asymmetric padding) are not on the hot path and are refused rather than silently rerouted."""
+    if not conv_supported(module):
+        raise BackendError(
+            f"conv2d: unsupported configuration on CUDA (groups={module.groups}, dilation={module.dilation}, "
+            f"padding={module.padding}, stride={module.stride}, padding_mode={module.padding_mode})"
+        )
+    return conv2d(x, module.weight, module.bias, int(module.stride[0]), int(module.padding[0]), **fused)
+
+
+def group_norm(x: Tensor, groups: int, gamma: Tensor, beta: Tensor, eps: float, silu: bool = False) -> Tensor:
+    _inference_only(x, gamma, beta)
+    return _ops.group_norm(x, groups, gamma, beta, eps, silu)
+
+
+def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    _inference_only(x, gamma, beta)
+    return _ops.layer_norm(x, gamma, beta, eps)
+
+
+def layer_norm_2d(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    """Channel-wise LN of an NCHW map = row LN over the NHWC pixels."""
+    _inference_only(x, gamma, beta)
+    nhwc = x.permute(0, 2, 3, 1)
+    return _ops.layer_norm(nhwc, gamma, beta, eps).permute(0, 3, 1, 2)
+
+
+def unary(x: Tensor, name: str) -> Tensor:
+    _inference_only(x)
+    return _ops.unary(x, _UNARY[name])
+
+
+def geglu(x: Tensor) -> Tensor:
+    _inference_only(x)
+    return _ops.geglu(x)
+
+
+def add(a: Tensor, b: Tensor, alpha: float = 1.0) -> Tensor:
+    _inference_only(a, b)
+    return _ops.add(a, b, alpha)
+
+
+def sdpa(
+    q: Tensor,
+    k: Tensor,
+    v: Tensor,
+    num_heads: int,
+    is_causal: bool = False,
+    *,
+    k2: Tensor | None = None,
+    v2: Tensor | None = None,
+    scale2: float = 0.0,
+) -> Tensor:
+    _inference_only(q, k, v)
+    return _ops.sdpa(q, k, v, k2, v2, num_heads, is_causal, scale2)
+
+
+def sam_attention(qkv: Tensor, rel_h: Tensor, rel_w: Tensor, num_heads: int) -> Tensor:
+    _inference_only(qkv, rel_h, rel_w)
+    return _ops.sam_attention(qkv, rel_h, rel_w, num_heads)

@@ -1,0 +1,4 @@
+from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1.model import StableDiffusion_1
+from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+
+__all__ = ["SD1UNet", "StableDiffusion_1"]
