@@ -1,0 +1,461 @@
+// HBM-bound kernels: GroupNorm(+SiLU) on NHWC, LayerNorm, unary activations, GEGLU, add,
+// plus the one-time weight packers.  All reductions use a fixed order (no atomics), so two
+// identical forwards are bit-identical (the reference pins this in
+// tests/foundationals/latent_diffusion/test_sd15_unet.py:21-37).
+#include "common.cuh"
+
+namespace rb200 {
+namespace {
+
+// ------------------------------------------------------------------------------ GroupNorm
+constexpr int GN_PIX = 128;  // pixels per block
+
+template <typename T, int V>
+__global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t HW, int C, int G,
+                                  int chunks) {
+  extern __shared__ float sm[];  // [lanes][C][2]
+  const int CV = C / V;
+  const int v = threadIdx.x, lane = threadIdx.y, lanes = blockDim.y;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int64_t p0 = int64_t(chunk) * GN_PIX;
+  const int64_t p1 = (p0 + GN_PIX < HW) ? p0 + GN_PIX : HW;
+  float s[V], q[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) s[e] = q[e] = 0.f;
+  const T* base = x + (int64_t(b) * HW) * C + int64_t(v) * V;
+  for (int64_t p = p0 + lane; p < p1; p += lanes) {
+    T vals[V];
+    if constexpr (V * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(vals) = *reinterpret_cast<const uint4*>(base + p * C);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) vals[e] = base[p * C + e];
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float f = to_f(vals[e]);
+      s[e] += f;
+      q[e] = fmaf(f, f, q[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    sm[(lane * C + v * V + e) * 2 + 0] = s[e];
+    sm[(lane * C + v * V + e) * 2 + 1] = q[e];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  if (t < G) {
+    const int cpg = C / G;
+    float ss = 0.f, qq = 0.f;
+    for (int l = 0; l < lanes; ++l)
+      for (int c = t * cpg; c < (t + 1) * cpg; ++c) {
+        ss += sm[(l * C + c) * 2 + 0];
+        qq += sm[(l * C + c) * 2 + 1];
+      }
+    float* out = part + ((int64_t(b) * chunks + chunk) * G + t) * 2;
+    out[0] = ss;
+    out[1] = qq;
+  }
+  (void)CV;
+}
+
+template <typename T, int V>
+__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ part,
+                                const T* __restrict__ gamma, const T* __restrict__ beta, int64_t HW, int C, int G,
+                                int chunks, float eps, int silu) {
+  extern __shared__ float sm[];  // mean[G], rstd[G]
+  const int v = threadIdx.x, lane = threadIdx.y, lanes = blockDim.y;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int cpg = C / G;
+  for (int g = t; g < G; g += nthreads) {
+    double ss = 0.0, qq = 0.0;
+    const float* src = part + (int64_t(b) * chunks * G + g) * 2;
+    for (int c = 0; c < chunks; ++c) {
+      ss += double(src[int64_t(c) * G * 2 + 0]);
+      qq += double(src[int64_t(c) * G * 2 + 1]);
+    }
+    const double n = double(HW) * double(cpg);
+    const double mean = ss / n;
+    double var = qq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sm[g] = float(mean);
+    sm[G + g] = float(1.0 / sqrt(var + double(eps)));
+  }
+  __syncthreads();
+  float ga[V], be[V], mu[V], rs[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int c = v * V + e;
+    ga[e] = to_f(gamma[c]);
+    be[e] = to_f(beta[c]);
+    mu[e] = sm[c / cpg];
+    rs[e] = sm[G + c / cpg];
+  }
+  const int64_t p0 = int64_t(chunk) * GN_PIX;
+  const int64_t p1 = (p0 + GN_PIX < HW) ? p0 + GN_PIX : HW;
+  const int64_t base = (int64_t(b) * HW) * C + int64_t(v) * V;
+  for (int64_t p = p0 + lane; p < p1; p += lanes) {
+    T vals[V];
+    if constexpr (V * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(vals) = *reinterpret_cast<const uint4*>(x + base + p * C);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) vals[e] = x[base + p * C + e];
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      float f = (to_f(vals[e]) - mu[e]) * rs[e] * ga[e] + be[e];
+      if (silu) f = silu_f(f);
+      vals[e] = from_f<T>(f);
+    }
+    if constexpr (V * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(y + base + p * C) = *reinterpret_cast<const uint4*>(vals);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) y[base + p * C + e] = vals[e];
+    }
+  }
+}
+
+template <typename T, int V>
+int gn_launch(cudaStream_t st, const T* x, T* y, int64_t B, int64_t HW, int C, int G, float eps, const T* gamma,
+              const T* beta, int silu, float* part) {
+  const int CV = C / V;
+  if (CV > 1024) RB200_FAIL(-1, "group_norm: C=%d too wide for this layout", C);
+  int lanes = 256 / CV;
+  if (lanes < 1) lanes = 1;
+  if (lanes > GN_PIX) lanes = GN_PIX;
+  while (CV * lanes < G) ++lanes;  // need at least G threads for the group reduce
+  const int chunks = int(ceil_div(HW, GN_PIX));
+  dim3 block(CV, lanes), grid(chunks, (unsigned)B);
+  const size_t sm1 = size_t(lanes) * C * 2 * sizeof(float);
+  if (sm1 > 200 * 1024) RB200_FAIL(-1, "group_norm: shared memory need %zu too large", sm1);
+  if (sm1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm1));
+  gn_partial_kernel<T, V><<<grid, block, sm1, st>>>(x, part, HW, C, G, chunks);
+  RB200_CHECK_LAUNCH("gn_partial");
+  gn_apply_kernel<T, V><<<grid, block, 2 * G * sizeof(float), st>>>(x, y, part, gamma, beta, HW, C, G, chunks, eps, silu);
+  RB200_CHECK_LAUNCH("gn_apply");
+  return 0;
+}
+
+template <typename T>
+int gn_dispatch(cudaStream_t st, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G, float eps,
+                const void* gamma, const void* beta, int silu, float* part) {
+  constexpr int VMAX = 16 / sizeof(T);
+  const bool aligned = (C % VMAX == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
+  if (aligned)
+    return gn_launch<T, VMAX>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part);
+  return gn_launch<T, 1>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part);
+}
+
+// ------------------------------------------------------------------------------ LayerNorm
+template <typename T>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C,
+                                                         float eps, const T* __restrict__ gamma,
+                                                         const T* __restrict__ beta, int vec_ok) {
+  constexpr int V = 16 / sizeof(T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  T* yr = y + row * C;
+  float s = 0.f;
+  if (vec_ok) {
+    for (int c = lane * V; c < C; c += 32 * V) {
+      Vec16<T> r = ld16(xr + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) s += to_f(r.v[e]);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+  }
+  const float mean = warp_sum(s) / float(C);
+  float q = 0.f;
+  if (vec_ok) {
+    for (int c = lane * V; c < C; c += 32 * V) {
+      Vec16<T> r = ld16(xr + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float d = to_f(r.v[e]) - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      const float d = to_f(xr[c]) - mean;
+      q = fmaf(d, d, q);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
+  if (vec_ok) {
+    for (int c = lane * V; c < C; c += 32 * V) {
+      Vec16<T> r = ld16(xr + c), g = ld16(gamma + c), bt = ld16(beta + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.v[e] = from_f<T>((to_f(r.v[e]) - mean) * rstd * to_f(g.v[e]) + to_f(bt.v[e]));
+      st16(yr + c, r);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) yr[c] = from_f<T>((to_f(xr[c]) - mean) * rstd * to_f(gamma[c]) + to_f(beta[c]));
+  }
+}
+
+// ---------------------------------------------------------------------------- elementwise
+__device__ __forceinline__ float unary_f(float x, int op) {
+  switch (op) {
+    case RB200_UNARY_SILU: return silu_f(x);
+    case RB200_UNARY_GELU: return gelu_erf(x);
+    case RB200_UNARY_GELU_TANH: return gelu_tanh(x);
+    case RB200_UNARY_GELU_SIGMOID: return x * sigmoid_f(1.702f * x);
+    case RB200_UNARY_RELU: return fmaxf(x, 0.f);
+    default: return sigmoid_f(x);
+  }
+}
+
+template <typename T>
+__global__ void unary_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, int op, int vec_ok) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t nv = n / V;
+    for (; i < nv; i += stride) {
+      Vec16<T> r = ld16(x + i * V);
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.v[e] = from_f<T>(unary_f(to_f(r.v[e]), op));
+      st16(y + i * V, r);
+    }
+    for (int64_t j = nv * V + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x); j < n; j += stride)
+      y[j] = from_f<T>(unary_f(to_f(x[j]), op));
+  } else {
+    for (; i < n; i += stride) y[i] = from_f<T>(unary_f(to_f(x[i]), op));
+  }
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n, float alpha,
+                           int vec_ok) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t nv = n / V;
+    for (; i < nv; i += stride) {
+      Vec16<T> r = ld16(a + i * V), s = ld16(b + i * V);
+#pragma unroll
+      for (int e = 0; e < V; ++e) r.v[e] = from_f<T>(fmaf(alpha, to_f(s.v[e]), to_f(r.v[e])));
+      st16(y + i * V, r);
+    }
+    for (int64_t j = nv * V + (int64_t(blockIdx.x) * blockDim.x + threadIdx.x); j < n; j += stride)
+      y[j] = from_f<T>(fmaf(alpha, to_f(b[j]), to_f(a[j])));
+  } else {
+    for (; i < n; i += stride) y[i] = from_f<T>(fmaf(alpha, to_f(b[i]), to_f(a[i])));
+  }
+}
+
+template <typename T>
+__global__ void geglu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t F, int vec_ok) {
+  constexpr int V = 16 / sizeof(T);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t fv = F / V, total = rows * fv;
+    for (; i < total; i += stride) {
+      const int64_t r = i / fv, c = (i - r * fv) * V;
+      Vec16<T> a = ld16(x + r * 2 * F + c), g = ld16(x + r * 2 * F + F + c);
+#pragma unroll
+      for (int e = 0; e < V; ++e) a.v[e] = from_f<T>(to_f(a.v[e]) * gelu_erf(to_f(g.v[e])));
+      st16(y + r * F + c, a);
+    }
+  } else {
+    const int64_t total = rows * F;
+    for (; i < total; i += stride) {
+      const int64_t r = i / F, c = i - r * F;
+      y[i] = from_f<T>(to_f(x[r * 2 * F + c]) * gelu_erf(to_f(x[r * 2 * F + F + c])));
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------- packers
+template <typename T>
+__global__ void conv_pack_kernel(const T* __restrict__ w, T* __restrict__ out, int64_t Cout, int64_t Cin, int RS) {
+  // out[t][n][c] = w[n][c][t]
+  const int64_t total = Cout * Cin * RS;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t c = i % Cin, n = (i / Cin) % Cout, t = i / (Cin * Cout);
+    out[i] = w[(n * Cin + c) * RS + t];
+  }
+}
+
+template <typename T>
+__global__ void geglu_pack_kernel(const T* __restrict__ w, const T* __restrict__ bias, T* __restrict__ wp,
+                                  T* __restrict__ bp, int64_t F, int64_t K) {
+  // packed row p: block = p / 32, j = p % 32; j < 16 -> value row block*16 + j, else gate row F + block*16 + j - 16
+  const int64_t total = 2 * F * K;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t p = i / K, k = i - p * K;
+    const int64_t blk = p / 32, j = p % 32;
+    const int64_t src = (j < 16) ? blk * 16 + j : F + blk * 16 + (j - 16);
+    wp[i] = w[src * K + k];
+    if (bias != nullptr && k == 0) bp[p] = bias[src];
+  }
+}
+
+struct LoraList { rb200_lora l[8]; };
+
+template <typename T>
+__global__ void lora_pack_kernel(const LoraList list, int n_lora, int64_t N, int64_t K,
+                                 T* __restrict__ down_cat, T* __restrict__ up_cat, float* __restrict__ colscale,
+                                 int r_pad) {
+  const rb200_lora* loras = list.l;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t t0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  // down_cat [r_pad, K]
+  for (int64_t i = t0; i < int64_t(r_pad) * K; i += stride) {
+    const int64_t r = i / K, k = i - r * K;
+    int64_t off = 0;
+    T val = from_f<T>(0.f);
+    for (int l = 0; l < n_lora; ++l) {
+      if (r < off + loras[l].rank) {
+        val = static_cast<const T*>(loras[l].down)[(r - off) * K + k];
+        break;
+      }
+      off += loras[l].rank;
+    }
+    down_cat[i] = val;
+  }
+  // up_cat [N, r_pad]
+  for (int64_t i = t0; i < N * r_pad; i += stride) {
+    const int64_t n = i / r_pad, r = i - n * r_pad;
+    int64_t off = 0;
+    T val = from_f<T>(0.f);
+    for (int l = 0; l < n_lora; ++l) {
+      if (r < off + loras[l].rank) {
+        val = static_cast<const T*>(loras[l].up)[n * loras[l].rank + (r - off)];
+        break;
+      }
+      off += loras[l].rank;
+    }
+    up_cat[i] = val;
+  }
+  for (int64_t r = t0; r < r_pad; r += stride) {
+    int64_t off = 0;
+    float sc = 0.f;
+    for (int l = 0; l < n_lora; ++l) {
+      if (r < off + loras[l].rank) {
+        sc = loras[l].scale;
+        break;
+      }
+      off += loras[l].rank;
+    }
+    colscale[r] = sc;
+  }
+}
+
+inline int ew_grid(int64_t work_items) {
+  int64_t blocks = ceil_div(work_items, 256);
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                                             \
+  switch (dtype) {                                                         \
+    case RB200_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }      \
+    case RB200_FP16: { using T = __half; __VA_ARGS__; break; }             \
+    case RB200_FP32: { using T = float; __VA_ARGS__; break; }              \
+    default: RB200_FAIL(-1, "bad dtype %d", dtype);                        \
+  }
+
+int group_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G,
+                    float eps, const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes) {
+  if (G <= 0 || C % G != 0) RB200_FAIL(-1, "group_norm: C=%lld not divisible by G=%d", (long long)C, G);
+  const size_t need = size_t(B) * size_t(ceil_div(HW, GN_PIX)) * size_t(G) * 2 * sizeof(float);
+  if (ws_bytes < need || ws == nullptr) RB200_FAIL(-1, "group_norm: workspace %zu < %zu", ws_bytes, need);
+  if (B > 65535) RB200_FAIL(-1, "group_norm: batch %lld too large", (long long)B);
+  DISPATCH_T(dtype, return gn_dispatch<T>(st, x, y, B, HW, C, G, eps, gamma, beta, silu, static_cast<float*>(ws)));
+  return 0;
+}
+
+size_t group_norm_ws(int64_t B, int64_t HW, int G) { return size_t(B) * size_t(ceil_div(HW, GN_PIX)) * size_t(G) * 2 * sizeof(float); }
+
+int layer_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows, int64_t C, float eps,
+                    const void* gamma, const void* beta) {
+  const int warps = 8;
+  const unsigned grid = (unsigned)ceil_div(rows, warps);
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    const int vec_ok = (C % V == 0) && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta);
+    layer_norm_kernel<T><<<grid, warps * 32, 0, st>>>((const T*)x, (T*)y, rows, int(C), eps, (const T*)gamma, (const T*)beta, vec_ok);
+  });
+  RB200_CHECK_LAUNCH("layer_norm");
+  return 0;
+}
+
+int unary_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t n, int op) {
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    const int vec_ok = aligned16(x) && aligned16(y);
+    unary_kernel<T><<<ew_grid(n / V + 1), 256, 0, st>>>((const T*)x, (T*)y, n, op, vec_ok);
+  });
+  RB200_CHECK_LAUNCH("unary");
+  return 0;
+}
+
+int add_impl(cudaStream_t st, int dtype, const void* a, const void* b, void* y, int64_t n, float alpha) {
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    const int vec_ok = aligned16(a) && aligned16(b) && aligned16(y);
+    add_kernel<T><<<ew_grid(n / V + 1), 256, 0, st>>>((const T*)a, (const T*)b, (T*)y, n, alpha, vec_ok);
+  });
+  RB200_CHECK_LAUNCH("add");
+  return 0;
+}
+
+int geglu_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows, int64_t F) {
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    const int vec_ok = (F % V == 0) && aligned16(x) && aligned16(y);
+    geglu_kernel<T><<<ew_grid(rows * F / V + 1), 256, 0, st>>>((const T*)x, (T*)y, rows, F, vec_ok);
+  });
+  RB200_CHECK_LAUNCH("geglu");
+  return 0;
+}
+
+int conv_pack_impl(cudaStream_t st, int dtype, const void* w, void* out, int64_t Cout, int64_t Cin, int R, int S) {
+  DISPATCH_T(dtype, conv_pack_kernel<T><<<ew_grid(Cout * Cin * R * S), 256, 0, st>>>((const T*)w, (T*)out, Cout, Cin, R * S));
+  RB200_CHECK_LAUNCH("conv_pack");
+  return 0;
+}
+
+int geglu_pack_impl(cudaStream_t st, int dtype, const void* w, const void* bias, void* wp, void* bp, int64_t F, int64_t K) {
+  if (F % 16 != 0) RB200_FAIL(-1, "geglu_pack: F=%lld must be a multiple of 16", (long long)F);
+  DISPATCH_T(dtype, geglu_pack_kernel<T><<<ew_grid(2 * F * K), 256, 0, st>>>((const T*)w, (const T*)bias, (T*)wp, (T*)bp, F, K));
+  RB200_CHECK_LAUNCH("geglu_pack");
+  return 0;
+}
+
+int lora_pack_impl(cudaStream_t st, int dtype, int n_lora, const rb200_lora* descs, int64_t N, int64_t K,
+                   void* down_cat, void* up_cat, float* colscale, int r_pad) {
+  if (n_lora < 1 || n_lora > 8) RB200_FAIL(-1, "lora_pack: 1..8 LoRAs per layer supported, got %d", n_lora);
+  LoraList list;
+  int total = 0;
+  for (int i = 0; i < n_lora; ++i) {
+    list.l[i] = descs[i];
+    total += descs[i].rank;
+  }
+  if (total > r_pad || r_pad % 64 != 0) RB200_FAIL(-1, "lora_pack: r_pad=%d must be a multiple of 64 and >= %d", r_pad, total);
+  const int64_t work = (N > K ? N : K) * r_pad;
+  DISPATCH_T(dtype, lora_pack_kernel<T><<<ew_grid(work), 256, 0, st>>>(list, n_lora, N, K, (T*)down_cat, (T*)up_cat, colscale, r_pad));
+  RB200_CHECK_LAUNCH("lora_pack");
+  return 0;
+}
+
+}  // namespace rb200

@@ -1,0 +1,375 @@
+"""GPU parity of every C-ABI kernel against a plain PyTorch fp32 evaluation of the same op on
+the CPU (inputs pre-rounded to the kernel dtype).  Both kernel families are exercised:
+mode 0 = auto (tcgen05 wherever the shape allows) and mode 1 = CUDA-core kernels only.
+
+Tolerance: eps(dtype) * max|ref| (tests/helpers.py) - i.e. output rounding + fp32 accumulation
+order; stated per test where a longer op chain needs a small multiple.
+"""
+
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.helpers import assert_close, rounded
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.bfloat16, torch.float16, torch.float32]
+
+
+@pytest.fixture(params=[0, 1], ids=["auto", "simt"])
+def kernel_mode(request, cuda_device):
+    from refiners_b200 import backend as B
+
+    prev = B.set_kernel_mode(request.param)
+    yield request.param
+    B.set_kernel_mode(prev)
+
+
+def _gen(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+LINEAR_SHAPES = [
+    # (M, K, N)
+    (256, 128, 256),
+    (1000, 320, 1280),   # ragged M
+    (16, 1280, 1280),    # timestep MLP: M smaller than a tile
+    (1232, 2048, 640),   # text K/V projection (77 * 16 rows)
+    (384, 64, 96),       # N not a multiple of 32
+    (130, 72, 40),       # K not a multiple of 64, N tail
+    (64, 36, 24),        # K % 8 != 0 -> CUDA-core path even in auto mode
+    (2048, 1280, 2560),  # several waves of 128x256 tiles
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("shape", LINEAR_SHAPES, ids=str)
+def test_linear_bias(cuda_device, kernel_mode, dtype, shape):
+    from refiners_b200 import backend as B
+
+    M, K, N = shape
+    x, w, b = _gen((M, K), 1), _gen((N, K), 2, K**-0.5), _gen((N,), 3)
+    ref = F.linear(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype))
+    with torch.no_grad():
+        y = B.linear(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype))
+    assert_close(y, ref, dtype, what=f"linear{shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
+def test_linear_3d_no_bias_residual(cuda_device, kernel_mode, dtype):
+    from refiners_b200 import backend as B
+
+    x, w, r = _gen((3, 100, 256), 4), _gen((512, 256), 5, 1 / 16), _gen((3, 100, 512), 6)
+    ref = F.linear(rounded(x, dtype), rounded(w, dtype)) + rounded(r, dtype)
+    with torch.no_grad():
+        y = B.linear(x.to(cuda_device, dtype), w.to(cuda_device, dtype), None, residual=r.to(cuda_device, dtype))
+    assert y.shape == (3, 100, 512)
+    assert_close(y, ref, dtype, what="linear+residual")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("epi", ["gelu", "silu"])
+def test_linear_activation_epilogue(cuda_device, kernel_mode, dtype, epi):
+    from refiners_b200 import backend as B
+
+    x, w, b = _gen((300, 256), 7), _gen((192, 256), 8, 1 / 16), _gen((192,), 9)
+    pre = F.linear(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype))
+    ref = F.gelu(pre) if epi == "gelu" else F.silu(pre)
+    code = B.EPI_GELU if epi == "gelu" else B.EPI_SILU
+    with torch.no_grad():
+        y = B.linear(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype), epilogue=code)
+    assert_close(y, ref, dtype, what=f"linear+{epi}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("shape", [(200, 128, 64), (1024, 1280, 5120), (77, 320, 1280)], ids=str)
+def test_linear_geglu(cuda_device, kernel_mode, dtype, shape):
+    """Linear(K -> 2F) + GLU(GeLU) fused (cross_attention.py:69-71 in the reference)."""
+    from refiners_b200 import backend as B
+
+    M, K, Fh = shape
+    x, w, b = _gen((M, K), 10), _gen((2 * Fh, K), 11, K**-0.5), _gen((2 * Fh,), 12)
+    pre = F.linear(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype))
+    a, g = pre.chunk(2, dim=-1)
+    ref = a * F.gelu(g)
+    with torch.no_grad():
+        y = B.linear_geglu(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype))
+    assert y.shape == (M, Fh)
+    assert_close(y, ref, dtype, scale=2.0, what=f"geglu{shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=str)
+@pytest.mark.parametrize("ranks", [(16,), (16, 16), (4, 8, 32)], ids=str)
+def test_linear_lora(cuda_device, kernel_mode, dtype, ranks):
+    """y = x W^T + b + sum_i s_i (x A_i^T) B_i^T (lora.py:383-448 in the reference), fp32 math."""
+    from refiners_b200 import backend as B
+
+    M, K, N = 500, 320, 640
+    x, w, b = _gen((M, K), 13), _gen((N, K), 14, K**-0.5), _gen((N,), 15)
+    ref = F.linear(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype))
+    loras = []
+    for i, r in enumerate(ranks):
+        down, up, s = _gen((r, K), 20 + i, 1 / r), _gen((N, r), 30 + i, 0.05), 0.5 + 0.7 * i
+        ref = ref + s * F.linear(F.linear(rounded(x, dtype), rounded(down, dtype)), rounded(up, dtype))
+        loras.append((down.to(cuda_device, dtype), up.to(cuda_device, dtype), s))
+    with torch.no_grad():
+        y = B.linear(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype), loras=loras)
+    # the rank-space intermediate is rounded to the activation dtype once: allow 3 eps
+    assert_close(y, ref, dtype, scale=3.0, what=f"lora{ranks}")
+
+
+CONV_CASES = [
+    # (B, Cin, H, W, Cout, k, stride, pad)
+    (2, 64, 16, 16, 128, 3, 1, 1),
+    (1, 320, 32, 32, 320, 3, 1, 1),
+    (2, 320, 32, 32, 640, 1, 1, 0),
+    (2, 64, 32, 32, 64, 3, 2, 1),     # Downsample (sampling.py:41-98)
+    (2, 4, 32, 32, 320, 3, 1, 1),     # UNet input conv: Cin = 4 -> CUDA-core path
+    (2, 320, 16, 16, 4, 3, 1, 1),     # UNet output conv: Cout = 4
+    (4, 128, 8, 8, 128, 3, 1, 1),     # 8x8 map: one tile spans two images
+    (1, 96, 24, 40, 80, 3, 1, 1),     # odd geometry
+    (1, 8, 64, 64, 32, 16, 16, 0),    # patch embedding style (kernel = stride = 16)
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("case", CONV_CASES, ids=str)
+def test_conv2d(cuda_device, kernel_mode, dtype, case):
+    from refiners_b200 import backend as B
+
+    Bn, Cin, H, W, Cout, k, stride, pad = case
+    x = _gen((Bn, Cin, H, W), 40)
+    w = _gen((Cout, Cin, k, k), 41, (Cin * k * k) ** -0.5)
+    b = _gen((Cout,), 42)
+    ref = F.conv2d(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype), stride=stride, padding=pad)
+    with torch.no_grad():
+        y = B.conv2d(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype), stride, pad)
+    assert y.shape == ref.shape
+    assert_close(y, ref, dtype, what=f"conv{case}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
+def test_conv2d_fused_terms(cuda_device, kernel_mode, dtype):
+    """conv + per-sample channel bias (RangeAdapter2d) + residual (ResidualBlock shortcut)."""
+    from refiners_b200 import backend as B
+
+    x, w, b = _gen((2, 64, 16, 16), 43), _gen((128, 64, 3, 3), 44, 1 / 24), _gen((128,), 45)
+    cb, r = _gen((2, 128), 46), _gen((2, 128, 16, 16), 47)
+    ref = F.conv2d(rounded(x, dtype), rounded(w, dtype), rounded(b, dtype), padding=1)
+    ref = ref + rounded(cb, dtype)[:, :, None, None] + rounded(r, dtype)
+    dev = lambda t: t.to(cuda_device, dtype)
+    with torch.no_grad():
+        y = B.conv2d(dev(x), dev(w), dev(b), 1, 1, chan_bias=dev(cb), residual=dev(r))
+    assert_close(y, ref, dtype, what="conv+chan_bias+residual")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("shape", [(2, 320, 16, 16), (1, 64, 7, 9), (2, 1920, 8, 8), (3, 32, 5, 5)], ids=str)
+def test_group_norm(cuda_device, dtype, silu, shape):
+    from refiners_b200 import backend as B
+
+    x = _gen(shape, 50) * 2 + 0.5
+    C = shape[1]
+    g, b = _gen((C,), 51) * 0.2 + 1, _gen((C,), 52) * 0.2
+    ref = F.group_norm(rounded(x, dtype), 32, rounded(g, dtype), rounded(b, dtype), eps=1e-5)
+    if silu:
+        ref = F.silu(ref)
+    with torch.no_grad():
+        y = B.group_norm(x.to(cuda_device, dtype), 32, g.to(cuda_device, dtype), b.to(cuda_device, dtype), 1e-5, silu=silu)
+    assert y.shape == ref.shape
+    assert_close(y, ref, dtype, scale=2.0, what=f"group_norm{shape}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("shape", [(2, 77, 1280), (5, 640), (3, 10, 100)], ids=str)
+def test_layer_norm(cuda_device, dtype, shape):
+    from refiners_b200 import backend as B
+
+    x = _gen(shape, 53) * 3 + 1
+    C = shape[-1]
+    g, b = _gen((C,), 54) * 0.2 + 1, _gen((C,), 55) * 0.2
+    ref = F.layer_norm(rounded(x, dtype), (C,), rounded(g, dtype), rounded(b, dtype), eps=1e-5)
+    with torch.no_grad():
+        y = B.layer_norm(x.to(cuda_device, dtype), g.to(cuda_device, dtype), b.to(cuda_device, dtype), 1e-5)
+    assert_close(y, ref, dtype, scale=2.0, what=f"layer_norm{shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
+def test_layer_norm_2d(cuda_device, dtype):
+    from refiners_b200 import backend as B
+
+    x = _gen((2, 256, 6, 5), 56)
+    g, b = _gen((256,), 57) * 0.2 + 1, _gen((256,), 58) * 0.2
+    xr = rounded(x, dtype)
+    mu = xr.mean(1, keepdim=True)
+    var = (xr - mu).pow(2).mean(1, keepdim=True)
+    ref = rounded(g, dtype)[:, None, None] * ((xr - mu) / torch.sqrt(var + 1e-6)) + rounded(b, dtype)[:, None, None]
+    with torch.no_grad():
+        y = B.layer_norm_2d(x.to(cuda_device, dtype), g.to(cuda_device, dtype), b.to(cuda_device, dtype), 1e-6)
+    assert y.shape == x.shape
+    assert_close(y, ref, dtype, scale=2.0, what="layer_norm_2d")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("op", ["silu", "gelu", "gelu_tanh", "gelu_sigmoid", "relu", "sigmoid"])
+def test_unary(cuda_device, dtype, op):
+    from refiners_b200 import backend as B
+
+    x = _gen((3, 1001), 59) * 3
+    xr = rounded(x, dtype)
+    ref = {
+        "silu": F.silu(xr), "gelu": F.gelu(xr), "gelu_tanh": F.gelu(xr, approximate="tanh"),
+        "gelu_sigmoid": xr * torch.sigmoid(1.702 * xr), "relu": F.relu(xr), "sigmoid": torch.sigmoid(xr),
+    }[op]
+    with torch.no_grad():
+        y = B.unary(x.to(cuda_device, dtype), op)
+    assert_close(y, ref, dtype, scale=2.0, what=op)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+def test_geglu_and_add(cuda_device, dtype):
+    from refiners_b200 import backend as B
+
+    x = _gen((4, 33, 2 * 120), 60)
+    a, g = rounded(x, dtype).chunk(2, dim=-1)
+    with torch.no_grad():
+        y = B.geglu(x.to(cuda_device, dtype))
+    assert_close(y, a * F.gelu(g), dtype, scale=2.0, what="geglu")
+    p, q = _gen((2, 64, 9, 9), 61), _gen((2, 64, 9, 9), 62)
+    with torch.no_grad():
+        s = B.add(p.to(cuda_device, dtype), q.to(cuda_device, dtype), 0.5)
+    assert_close(s, rounded(p, dtype) + 0.5 * rounded(q, dtype), dtype, what="add")
+
+
+SDPA_CASES = [
+    # (B, H, Sq, Sk, D)
+    (2, 4, 64, 64, 64),
+    (1, 10, 256, 256, 64),
+    (2, 5, 200, 77, 64),     # cross-attention on 77 text tokens, ragged Sq
+    (1, 8, 96, 50, 40),      # SD1 head dims
+    (1, 8, 40, 40, 80),
+    (1, 2, 33, 65, 160),
+    (2, 3, 128, 4, 64),      # IP-Adapter token count
+    (1, 1, 1, 1, 64),
+]
+
+
+def _sdpa_ref(q, k, v, H, causal=False):
+    B_, Sq, C = q.shape
+    split = lambda t: t.reshape(t.shape[0], t.shape[1], H, C // H).transpose(1, 2)
+    o = F.scaled_dot_product_attention(split(q), split(k), split(v), is_causal=causal)
+    return o.transpose(1, 2).reshape(B_, Sq, C)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("case", SDPA_CASES, ids=str)
+def test_sdpa(cuda_device, kernel_mode, dtype, case):
+    from refiners_b200 import backend as B
+
+    Bn, H, Sq, Sk, D = case
+    q, k, v = _gen((Bn, Sq, H * D), 70), _gen((Bn, Sk, H * D), 71), _gen((Bn, Sk, H * D), 72)
+    ref = _sdpa_ref(rounded(q, dtype), rounded(k, dtype), rounded(v, dtype), H)
+    dev = lambda t: t.to(cuda_device, dtype)
+    with torch.no_grad():
+        y = B.sdpa(dev(q), dev(k), dev(v), H)
+    # P is rounded to the operand dtype before the PV product in the tensor-core kernel: 4 eps
+    assert_close(y, ref, dtype, scale=4.0, what=f"sdpa{case}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
+def test_sdpa_causal(cuda_device, kernel_mode, dtype):
+    from refiners_b200 import backend as B
+
+    q, k, v = _gen((2, 77, 128), 73), _gen((2, 77, 128), 74), _gen((2, 77, 128), 75)
+    ref = _sdpa_ref(rounded(q, dtype), rounded(k, dtype), rounded(v, dtype), 2, causal=True)
+    dev = lambda t: t.to(cuda_device, dtype)
+    with torch.no_grad():
+        y = B.sdpa(dev(q), dev(k), dev(v), 2, True)
+    assert_close(y, ref, dtype, scale=4.0, what="sdpa causal")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=str)
+@pytest.mark.parametrize("tokens", [4, 16])
+def test_sdpa_dual_kv(cuda_device, kernel_mode, dtype, tokens):
+    """IP-Adapter: SDPA(q, k_text, v_text) + s * SDPA(q, k_img, v_img), two softmaxes
+    (image_prompt.py:237-309 in the reference)."""
+    from refiners_b200 import backend as B
+
+    H, D = 5, 64
+    q, k, v = _gen((2, 192, H * D), 76), _gen((2, 77, H * D), 77), _gen((2, 77, H * D), 78)
+    k2, v2 = _gen((2, tokens, H * D), 79), _gen((2, tokens, H * D), 80)
+    r = lambda t: rounded(t, dtype)
+    ref = _sdpa_ref(r(q), r(k), r(v), H) + 0.6 * _sdpa_ref(r(q), r(k2), r(v2), H)
+    dev = lambda t: t.to(cuda_device, dtype)
+    with torch.no_grad():
+        y = B.sdpa(dev(q), dev(k), dev(v), H, k2=dev(k2), v2=dev(v2), scale2=0.6)
+    assert_close(y, ref, dtype, scale=4.0, what="sdpa dual kv")
+
+
+def test_sdpa_strided_views(cuda_device, kernel_mode):
+    """q/k/v as column slices of one fused projection (no copies made)."""
+    from refiners_b200 import backend as B
+
+    dtype = torch.bfloat16
+    qkv = _gen((2, 100, 3 * 128), 81)
+    q, k, v = rounded(qkv, dtype).chunk(3, dim=-1)
+    ref = _sdpa_ref(q, k, v, 2)
+    dq, dk, dv = qkv.to(cuda_device, dtype).chunk(3, dim=-1)
+    with torch.no_grad():
+        y = B.sdpa(dq, dk, dv, 2)
+    assert_close(y, ref, dtype, scale=4.0, what="sdpa strided")
+
+
+def test_requires_no_grad(cuda_device):
+    from refiners_b200 import backend as B
+
+    x = torch.randn(4, 64, device=cuda_device, requires_grad=True)
+    w = torch.randn(64, 64, device=cuda_device)
+    with pytest.raises(B.BackendError):
+        B.linear(x, w)
+
+
+def test_error_reporting(cuda_device):
+    from refiners_b200 import backend as B
+
+    x = torch.randn(4, 64, device=cuda_device)
+    w = torch.randn(64, 32, device=cuda_device)
+    with torch.no_grad(), pytest.raises(B.BackendError):
+        B.linear(x, w)
+
+
+def test_launch_counter_and_determinism(cuda_device):
+    from refiners_b200 import backend as B
+
+    x = torch.randn(512, 256, device=cuda_device, dtype=torch.bfloat16)
+    w = torch.randn(256, 256, device=cuda_device, dtype=torch.bfloat16)
+    before = B.launch_count()
+    with torch.no_grad():
+        a = B.linear(x, w)
+        b = B.linear(x, w)
+    assert B.launch_count() - before == 2
+    assert torch.equal(a, b)
+
+
+def test_cuda_graph_capture(cuda_device):
+    """Every op is capture-safe (no sync, no foreign allocation): replay reproduces eager."""
+    from refiners_b200 import backend as B
+
+    x = torch.randn(256, 320, device=cuda_device, dtype=torch.bfloat16)
+    w = torch.randn(640, 320, device=cuda_device, dtype=torch.bfloat16) * 0.05
+    g, b = torch.ones(640, device=cuda_device, dtype=torch.bfloat16), torch.zeros(640, device=cuda_device, dtype=torch.bfloat16)
+    with torch.no_grad():
+        eager = B.layer_norm(B.linear(x, w), g, b, 1e-5)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = B.layer_norm(B.linear(x, w), g, b, 1e-5)
+        x.copy_(x * 1.0)
+        graph.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, eager)
