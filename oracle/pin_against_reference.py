@@ -1,0 +1,261 @@
+"""Pin the oracle against the REAL reference and (re)generate tests/golden/*.safetensors.
+
+Run only where /root/reference is mounted (the build container):
+
+    python oracle/pin_against_reference.py            # check + write fixtures
+    python oracle/pin_against_reference.py --check    # check only
+
+For every case the reference's own modules (imported unmodified from /root/reference/src) are
+evaluated in fp32 on the CPU; the oracle restatement must agree within 1e-5 * max|ref|, and the
+reference's inputs/outputs (plus weights, for the small cases) are stored as fixtures.  The GPU
+box has no /root/reference: tests there read only the committed fixtures.
+TEST INFRASTRUCTURE - see oracle/__init__.py.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_SRC = Path("/root/reference/src")
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def _import_reference():
+    if not REF_SRC.exists():
+        raise SystemExit("/root/reference is not mounted here: nothing to pin against")
+    stub = Path("/tmp/rb200_refstub")
+    meta = stub / "refiners-0.0.0.dist-info"
+    meta.mkdir(parents=True, exist_ok=True)
+    (meta / "METADATA").write_text("Metadata-Version: 2.1\nName: refiners\nVersion: 0.0.0\nRequires-Dist: torch\n")
+    for p in (str(REF_SRC), str(stub), str(ROOT)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import refiners.fluxion.layers as rfl  # noqa: F401
+
+    return rfl
+
+
+def _close(name: str, got: torch.Tensor, want: torch.Tensor, rel: float = 1e-5) -> None:
+    err = (got - want).abs().max().item()
+    tol = rel * max(want.abs().max().item(), 1e-3)
+    status = "ok " if err <= tol else "FAIL"
+    print(f"  [{status}] {name}: max abs diff {err:.3e} (tol {tol:.3e})")
+    if err > tol:
+        raise SystemExit(f"oracle disagrees with the reference on {name}")
+
+
+def main(write: bool) -> None:
+    rfl = _import_reference()
+    from safetensors.torch import save_file
+
+    from oracle import euler as oeuler
+    from oracle import ops, sam as osam, unet as ounet
+    from oracle.weights import keyed_state_dict
+
+    torch.manual_seed(1234)
+    g = lambda *s: torch.randn(*s)
+    out: dict[str, dict[str, torch.Tensor]] = {}
+
+    with torch.no_grad():
+        # ------------------------------------------------------------------ leaf ops
+        print("leaf ops")
+        fx: dict[str, torch.Tensor] = {}
+        lin = rfl.Linear(48, 40)
+        x = g(3, 7, 48)
+        fx.update({"linear.x": x, "linear.w": lin.weight, "linear.b": lin.bias, "linear.y": lin(x)})
+        _close("Linear", ops.linear(x, lin.weight, lin.bias), fx["linear.y"])
+
+        for tag, (k, s, p) in {"3x3": (3, 1, 1), "3x3s2": (3, 2, 1), "1x1": (1, 1, 0)}.items():
+            conv = rfl.Conv2d(8, 12, kernel_size=k, stride=s, padding=p)
+            x = g(2, 8, 10, 12)
+            fx.update({f"conv{tag}.x": x, f"conv{tag}.w": conv.weight, f"conv{tag}.b": conv.bias, f"conv{tag}.y": conv(x)})
+            _close(f"Conv2d {tag}", ops.conv2d(x, conv.weight, conv.bias, s, p), fx[f"conv{tag}.y"])
+
+        gn = rfl.GroupNorm(64, 32, eps=1e-6)
+        gn.weight.copy_(1 + 0.1 * g(64)); gn.bias.copy_(0.1 * g(64))
+        x = g(2, 64, 6, 5) * 2 + 0.3
+        fx.update({"gn.x": x, "gn.w": gn.weight, "gn.b": gn.bias, "gn.y": gn(x), "gn_silu.y": rfl.SiLU()(gn(x))})
+        _close("GroupNorm", ops.group_norm(x, 32, gn.weight, gn.bias, 1e-6), fx["gn.y"])
+        _close("GroupNorm+SiLU", ops.silu(ops.group_norm(x, 32, gn.weight, gn.bias, 1e-6)), fx["gn_silu.y"])
+
+        ln = rfl.LayerNorm(40)
+        ln.weight.copy_(1 + 0.1 * g(40)); ln.bias.copy_(0.1 * g(40))
+        x = g(2, 9, 40) * 3
+        fx.update({"ln.x": x, "ln.w": ln.weight, "ln.b": ln.bias, "ln.y": ln(x)})
+        _close("LayerNorm", ops.layer_norm(x, ln.weight, ln.bias, 1e-5), fx["ln.y"])
+
+        ln2 = rfl.LayerNorm2d(16)
+        ln2.weight.copy_(1 + 0.1 * g(16)); ln2.bias.copy_(0.1 * g(16))
+        x = g(2, 16, 5, 4)
+        fx.update({"ln2d.x": x, "ln2d.w": ln2.weight, "ln2d.b": ln2.bias, "ln2d.y": ln2(x)})
+        _close("LayerNorm2d", ops.layer_norm_2d(x, ln2.weight, ln2.bias, 1e-6), fx["ln2d.y"])
+
+        x = g(4, 50) * 3
+        fx.update({"act.x": x, "silu.y": rfl.SiLU()(x), "gelu.y": rfl.GeLU()(x), "glu.y": rfl.GLU(rfl.GeLU())(x)})
+        _close("SiLU", ops.silu(x), fx["silu.y"])
+        _close("GeLU", ops.gelu(x), fx["gelu.y"])
+        _close("GLU(GeLU)", ops.glu_gelu(x), fx["glu.y"])
+
+        sd = rfl.ScaledDotProductAttention(num_heads=4)
+        q, k, v = g(2, 11, 64), g(2, 7, 64), g(2, 7, 64)
+        fx.update({"sdpa.q": q, "sdpa.k": k, "sdpa.v": v, "sdpa.y": sd(q, k, v)})
+        _close("ScaledDotProductAttention", ops.sdpa(q, k, v, 4), fx["sdpa.y"])
+        sdc = rfl.ScaledDotProductAttention(num_heads=2, is_causal=True)
+        q = g(1, 9, 32)
+        fx.update({"sdpa_causal.q": q, "sdpa_causal.y": sdc(q, q, q)})
+        _close("ScaledDotProductAttention causal", ops.sdpa(q, q, q, 2, True), fx["sdpa_causal.y"])
+
+        from refiners.fluxion.adapters.lora import LinearLora, LoraAdapter
+
+        base = rfl.Linear(48, 40)
+        holder = rfl.Chain(base)
+        l1, l2 = LinearLora("a", in_features=48, out_features=40, rank=4, scale=1.0), LinearLora("b", in_features=48, out_features=40, rank=8, scale=1.4)
+        for l in (l1, l2):
+            l.up.weight.copy_(0.05 * g(*l.up.weight.shape))
+        LoraAdapter(base, l1, l2).inject(holder)
+        x = g(5, 48)
+        fx.update({"lora.x": x, "lora.w": base.weight, "lora.b": base.bias, "lora.y": holder(x),
+                   "lora.down1": l1.down.weight, "lora.up1": l1.up.weight, "lora.down2": l2.down.weight, "lora.up2": l2.up.weight})
+        _close("LoraAdapter", ops.lora_linear(x, base.weight, base.bias, [(l1.down.weight, l1.up.weight, 1.0), (l2.down.weight, l2.up.weight, 1.4)]), fx["lora.y"])
+        out["ops"] = fx
+
+        # -------------------------------------------------------------------- blocks
+        print("blocks (weights stored in the fixture)")
+        from refiners.foundationals.latent_diffusion.cross_attention import CrossAttentionBlock2d
+        from refiners.foundationals.latent_diffusion.range_adapter import RangeAdapter2d
+        from refiners.foundationals.latent_diffusion.unet import ResidualBlock
+
+        fx = {}
+        for tag, (cin, cout) in {"res_same": (64, 64), "res_proj": (64, 96)}.items():
+            rb = ResidualBlock(cin, cout)
+            body = rb.layer("Chain", rfl.Chain)
+            RangeAdapter2d(target=body.layer("Conv2d_1", rfl.Conv2d), channels=cout, embedding_dim=32, context_key="timestep_embedding").inject(body)
+            top = rfl.Chain(rb)
+            temb, x = g(2, 32), g(2, cin, 8, 8)
+            top.set_context("range_adapter", {"timestep_embedding": temb})
+            y = top(x)
+            sdict = {f"{tag}.sd.ResidualBlock.{k}": v for k, v in rb.state_dict().items()}
+            fx.update(sdict)
+            fx.update({f"{tag}.x": x, f"{tag}.temb": temb, f"{tag}.y": y})
+            _close(f"ResidualBlock {cin}->{cout}", ounet.residual_block(rb.state_dict(prefix="ResidualBlock."), "ResidualBlock", x, temb), y)
+        for tag, linear_proj in {"xattn_linear": True, "xattn_conv": False}.items():
+            ca = CrossAttentionBlock2d(64, context_embedding_dim=48, context_key="ctx", num_attention_heads=2,
+                                       num_attention_layers=2, use_bias=False, use_linear_projection=linear_proj)
+            ctx, x = g(2, 5, 48), g(2, 64, 4, 6)
+            ca.set_context("cross_attention_block", {"ctx": ctx})
+            y = ca(x)
+            fx.update({f"{tag}.sd.{k}": v for k, v in ca.state_dict().items()})
+            fx.update({f"{tag}.x": x, f"{tag}.ctx": ctx, f"{tag}.y": y})
+            _close(f"CrossAttentionBlock2d linear={linear_proj}", ounet.cross_attention_2d(ca.state_dict(prefix="X."), "X", x, ctx, 2, 2, linear_proj), y)
+        out["blocks"] = fx
+
+        # -------------------------------------------------------------------- solver
+        print("Euler solver")
+        from refiners.foundationals.latent_diffusion.solvers import Euler
+
+        fx = {}
+        ref_solver = Euler(num_inference_steps=30)
+        mine = oeuler.EulerSchedule(30)
+        x, eps = g(2, 4, 8, 8), g(2, 4, 8, 8)
+        fx.update({"euler.sigmas": ref_solver.sigmas, "euler.timesteps": ref_solver.timesteps, "euler.x": x, "euler.eps": eps,
+                   "euler.scaled_init": ref_solver.scale_model_input(x, -1), "euler.scaled_7": ref_solver.scale_model_input(x, 7),
+                   "euler.step_7": ref_solver(x, predicted_noise=eps, step=7), "euler.step_29": ref_solver(x, predicted_noise=eps, step=29)})
+        _close("sigmas", mine.sigmas, ref_solver.sigmas)
+        _close("timesteps", mine.timesteps, ref_solver.timesteps)
+        _close("scale_model_input(-1)", mine.scale_model_input(x, -1), fx["euler.scaled_init"])
+        _close("scale_model_input(7)", mine.scale_model_input(x, 7), fx["euler.scaled_7"])
+        _close("update(7)", mine.update(x, eps, 7), fx["euler.step_7"])
+        _close("update(29)", mine.update(x, eps, 29), fx["euler.step_29"])
+        bf = Euler(num_inference_steps=30).to(dtype=torch.bfloat16)  # how LatentDiffusionModel casts it (model.py:33)
+        fx["euler.sigmas_bf16"] = bf.sigmas
+        out["euler"] = fx
+
+        # ----------------------------------------------------------------- full UNets
+        print("full UNets (weights regenerated from oracle.weights.keyed_state_dict, only I/O stored)")
+        from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+        from refiners.foundationals.latent_diffusion.stable_diffusion_xl.unet import SDXLUNet
+
+        fx = {}
+        unet = SD1UNet(4, device="meta")
+        shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        sdict = keyed_state_dict(shapes, seed=1)
+        unet = SD1UNet(4)
+        unet.load_state_dict(sdict)
+        x, ts, ctx = g(1, 4, 32, 32), torch.tensor([[500]]), g(1, 77, 768)
+        unet.set_timestep(ts); unet.set_clip_text_embedding(ctx)
+        y = unet(x)
+        fx.update({"sd1.x": x, "sd1.timestep": ts, "sd1.ctx": ctx, "sd1.y": y})
+        _close("SD1UNet", ounet.sd1_unet(sdict, x, ts, ctx), y)
+        del unet, sdict
+
+        unet = SDXLUNet(4, device="meta")
+        shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        sdict = keyed_state_dict(shapes, seed=2)
+        unet = SDXLUNet(4)
+        unet.load_state_dict(sdict)
+        x, ts = g(2, 4, 32, 32), torch.tensor([981.0])
+        ctx, pooled = g(2, 77, 2048), g(2, 1280)
+        ids = torch.tensor([[1024, 1024, 0, 0, 1024, 1024]]).repeat(2, 1)
+        unet.set_timestep(ts); unet.set_clip_text_embedding(ctx); unet.set_pooled_text_embedding(pooled); unet.set_time_ids(ids)
+        y = unet(x)
+        fx.update({"sdxl.x": x, "sdxl.timestep": ts, "sdxl.ctx": ctx, "sdxl.pooled": pooled, "sdxl.time_ids": ids, "sdxl.y": y})
+        _close("SDXLUNet", ounet.sdxl_unet(sdict, x, ts, ctx, pooled, ids), y)
+        del unet, sdict
+        out["unets"] = fx
+
+        # ------------------------------------------------------------------------ SAM
+        print("SAM ViT blocks")
+        from refiners.foundationals.segment_anything.image_encoder import (
+            FusedSelfAttention,
+            Neck,
+            PatchEncoder,
+            TransformerLayer,
+        )
+
+        fx = {}
+        fa = FusedSelfAttention(embedding_dim=32, spatial_size=(6, 6), num_heads=2)
+        for prm in (fa.RelativePositionAttention.horizontal_embedding, fa.RelativePositionAttention.vertical_embedding):
+            prm.copy_(0.3 * g(*prm.shape))
+        x = g(3, 6, 6, 32)
+        y = fa(x)
+        fx.update({f"fsa.sd.{k}": v for k, v in fa.state_dict().items()})
+        fx.update({"fsa.x": x, "fsa.y": y})
+        _close("FusedSelfAttention", osam.fused_self_attention(fa.state_dict(prefix="A."), "A", x, 2), y)
+        for tag, window in {"layer_win": 4, "layer_global": None}.items():
+            tl = TransformerLayer(embedding_dim=32, num_heads=2, feedforward_dim=64, image_embedding_size=(10, 10), window_size=window)
+            att = tl.layer(("Residual_1", "FusedSelfAttention", "RelativePositionAttention"), rfl.Module)
+            for prm in (att.horizontal_embedding, att.vertical_embedding):
+                prm.copy_(0.3 * g(*prm.shape))
+            x = g(2, 10, 10, 32)
+            y = tl(x)
+            fx.update({f"{tag}.sd.{k}": v for k, v in tl.state_dict().items()})
+            fx.update({f"{tag}.x": x, f"{tag}.y": y})
+            _close(f"TransformerLayer window={window}", osam.transformer_layer(tl.state_dict(prefix="L."), "L", x, 2, window), y)
+        pe = PatchEncoder(3, 32, patch_size=16)
+        nk = Neck(in_channels=32)
+        x = g(1, 3, 64, 64)
+        y = pe(x)
+        fx.update({f"patch.sd.{k}": v for k, v in pe.state_dict().items()})
+        fx.update({"patch.x": x, "patch.y": y})
+        _close("PatchEncoder", osam.patch_encoder(pe.state_dict(prefix="P."), "P", x), y)
+        z = g(1, 4, 4, 32)
+        yn = nk(z)
+        fx.update({f"neck.sd.{k}": v for k, v in nk.state_dict().items()})
+        fx.update({"neck.x": z, "neck.y": yn})
+        _close("Neck", osam.neck(nk.state_dict(prefix="N."), "N", z), yn)
+        out["sam"] = fx
+
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        for name, tensors in out.items():
+            path = GOLDEN / f"{name}.safetensors"
+            save_file({k: v.detach().contiguous().clone() for k, v in tensors.items()}, str(path))
+            print(f"wrote {path.relative_to(ROOT)} ({path.stat().st_size / 1024:.0f} KiB, {len(tensors)} tensors)")
+
+
+if __name__ == "__main__":
+    main(write="--check" not in sys.argv)

@@ -1,0 +1,196 @@
+"""Functional restatement of the SD1.5 and SDXL UNet forward passes over a reference state dict.
+
+The functions walk explicit block tables (not a module tree) and read weights by their
+reference state-dict keys, so they are independent both of the reference's Chain machinery and
+of refiners_b200's fluxion mirror.  TEST INFRASTRUCTURE - see oracle/__init__.py.
+
+Reference (paths under /root/reference/src/refiners/foundationals/latent_diffusion/):
+  unet.py:6-79                      ResidualBlock / ResidualAccumulator / ResidualConcatenator
+  range_adapter.py:11-86            sinusoidal embedding, RangeEncoder, RangeAdapter2d
+  cross_attention.py:25-175         CrossAttentionBlock / CrossAttentionBlock2d
+  stable_diffusion_1/unet.py:16-249 SD1UNet
+  stable_diffusion_xl/unet.py:20-351 SDXLUNet
+"""
+
+from __future__ import annotations
+
+from typing import Mapping
+
+import torch
+from torch import Tensor
+
+from oracle import ops
+
+SD = Mapping[str, Tensor]
+
+
+def _lin(sd: SD, prefix: str, x: Tensor) -> Tensor:
+    return ops.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+
+
+def _conv(sd: SD, prefix: str, x: Tensor, stride: int = 1, padding: int = 0) -> Tensor:
+    return ops.conv2d(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride=stride, padding=padding)
+
+
+def range_encoder(sd: SD, prefix: str, timestep: Tensor, dtype: torch.dtype) -> Tensor:
+    """sinusoid(320) -> cast -> Linear -> SiLU -> Linear  (range_adapter.py:25-44)."""
+    e = ops.sinusoidal_embedding(timestep, 320).to(dtype)
+    return _lin(sd, prefix + ".Linear_2", ops.silu(_lin(sd, prefix + ".Linear_1", e)))
+
+
+def residual_block(sd: SD, prefix: str, x: Tensor, temb: Tensor, eps: float = 1e-5) -> Tensor:
+    """unet.py:6-51 with the RangeAdapter2d injected around the first conv (sdxl/unet.py:286-295):
+    h = conv1(silu(gn1(x))) + Linear(silu(temb))[:, :, None, None]; h = conv2(silu(gn2(h)));
+    out = h + shortcut(x)."""
+    c = prefix + ".Chain"
+    h = ops.silu(ops.group_norm(x, 32, sd[c + ".GroupNorm_1.weight"], sd[c + ".GroupNorm_1.bias"], eps))
+    h = _conv(sd, c + ".RangeAdapter2d.Conv2d", h, padding=1)
+    t = _lin(sd, c + ".RangeAdapter2d.Chain.Linear", ops.silu(temb))
+    h = h + t.reshape(t.shape[0], -1, 1, 1)
+    h = ops.silu(ops.group_norm(h, 32, sd[c + ".GroupNorm_2.weight"], sd[c + ".GroupNorm_2.bias"], eps))
+    h = _conv(sd, c + ".Conv2d", h, padding=1)
+    shortcut = _conv(sd, prefix + ".Conv2d", x) if (prefix + ".Conv2d.weight") in sd else x
+    return h + shortcut
+
+
+def attention(sd: SD, prefix: str, q_in: Tensor, kv_in: Tensor, heads: int) -> Tensor:
+    """fl.Attention: Distribute(Wq, Wk, Wv) -> SDPA -> Wo  (fluxion/layers/attentions.py:205-316)."""
+    q = _lin(sd, prefix + ".Distribute.Linear_1", q_in)
+    k = _lin(sd, prefix + ".Distribute.Linear_2", kv_in)
+    v = _lin(sd, prefix + ".Distribute.Linear_3", kv_in)
+    return _lin(sd, prefix + ".Linear", ops.sdpa(q, k, v, heads))
+
+
+def cross_attention_block(sd: SD, prefix: str, x: Tensor, context: Tensor, heads: int) -> Tensor:
+    """cross_attention.py:25-73: three pre-LN residual branches (self-attn, cross-attn, GEGLU MLP)."""
+    r1, r2, r3 = prefix + ".Residual_1", prefix + ".Residual_2", prefix + ".Residual_3"
+    h = ops.layer_norm(x, sd[r1 + ".LayerNorm.weight"], sd[r1 + ".LayerNorm.bias"], 1e-5)
+    x = x + attention(sd, r1 + ".SelfAttention", h, h, heads)
+    h = ops.layer_norm(x, sd[r2 + ".LayerNorm.weight"], sd[r2 + ".LayerNorm.bias"], 1e-5)
+    x = x + attention(sd, r2 + ".Attention", h, context, heads)
+    h = ops.layer_norm(x, sd[r3 + ".LayerNorm.weight"], sd[r3 + ".LayerNorm.bias"], 1e-5)
+    h = _lin(sd, r3 + ".Linear_2", ops.glu_gelu(_lin(sd, r3 + ".Linear_1", h)))
+    return x + h
+
+
+def cross_attention_2d(sd: SD, prefix: str, x: Tensor, context: Tensor, heads: int, layers: int, linear_proj: bool) -> Tensor:
+    """cross_attention.py:92-175: GN(eps 1e-6) -> project in -> [B, HW, C] -> N blocks -> project out,
+    residual around everything.  SDXL projects with Linear, SD1.5 with 1x1 conv."""
+    B, C, H, W = x.shape
+    c1, c2, c3 = prefix + ".Chain_1", prefix + ".Chain_2", prefix + ".Chain_3"
+    h = ops.group_norm(x, 32, sd[c1 + ".GroupNorm.weight"], sd[c1 + ".GroupNorm.bias"], 1e-6)
+    if linear_proj:
+        h = _lin(sd, c1 + ".Linear", h.flatten(2).transpose(1, 2))
+    else:
+        h = _conv(sd, c1 + ".Conv2d", h).flatten(2).transpose(1, 2)
+    for i in range(layers):
+        name = c2 + (".CrossAttentionBlock" if layers == 1 else f".CrossAttentionBlock_{i + 1}")
+        h = cross_attention_block(sd, name, h, context, heads)
+    if linear_proj:
+        h = _lin(sd, c3 + ".Linear", h).transpose(1, 2).reshape(B, C, H, W)
+    else:
+        h = _conv(sd, c3 + ".Conv2d", h.transpose(1, 2).reshape(B, C, H, W))
+    return h + x
+
+
+# ------------------------------------------------------------------------------------ SD 1.5
+# (kind, *args): "res" = ResidualBlock(+attention?), "down", per reference DownBlocks/UpBlocks
+_SD1_DOWN = [("in",), ("res", True), ("res", True), ("down",), ("res", True), ("res", True), ("down",),
+             ("res", True), ("res", True), ("down",), ("res", False), ("res", False)]
+_SD1_UP = [(False, False), (False, False), (False, True), (True, False), (True, False), (True, True),
+           (True, False), (True, False), (True, True), (True, False), (True, False), (True, False)]
+
+
+def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor) -> Tensor:
+    """SD1UNet forward (stable_diffusion_1/unet.py:165-249): 12 down entries each recording a
+    skip, middle block added to the last skip, 12 up entries each consuming one skip."""
+    dtype = x.dtype
+    temb = range_encoder(sd, "TimestepEncoder.RangeEncoder", timestep, dtype)
+    skips: list[Tensor] = []
+    h = x
+    for i, entry in enumerate(_SD1_DOWN):
+        p = f"DownBlocks.Chain_{i + 1}"
+        if entry[0] == "in":
+            h = _conv(sd, p + ".Conv2d", h, padding=1)
+        elif entry[0] == "down":
+            h = _conv(sd, p + ".Downsample.Conv2d", h, stride=2, padding=1)
+        else:
+            h = residual_block(sd, p + ".ResidualBlock", h, temb)
+            if entry[1]:
+                h = cross_attention_2d(sd, p + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
+        skips.append(h)  # ResidualAccumulator: residuals[n] = x + 0.0
+    m = "Sum.MiddleBlock"
+    mid = residual_block(sd, m + ".ResidualBlock_1", h, temb)
+    mid = cross_attention_2d(sd, m + ".CLIPLCrossAttention", mid, clip_text_embedding, 8, 1, False)
+    mid = residual_block(sd, m + ".ResidualBlock_2", mid, temb)
+    # Sum(UseContext residuals[-1], MiddleBlock): the 13th residual slot is never written by the
+    # plain UNet (it exists for ControlNet), so this adds the initial 0.0
+    h = 0.0 + mid
+    for n, (attn, up) in enumerate(_SD1_UP):
+        p = f"UpBlocks.Chain_{n + 1}"
+        h = torch.cat([h, skips[-n - 1]], dim=1)  # ResidualConcatenator(-n-2) over 12 skips + 1 spare slot
+        h = residual_block(sd, p + ".ResidualBlock", h, temb)
+        if attn:
+            h = cross_attention_2d(sd, p + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
+        if up:
+            h = ops.nearest_upsample(h, (h.shape[-2] * 2, h.shape[-1] * 2))
+            h = _conv(sd, p + ".Upsample.Conv2d", h, padding=1)
+    h = ops.silu(ops.group_norm(h, 32, sd["Chain.GroupNorm.weight"], sd["Chain.GroupNorm.bias"], 1e-5))
+    return _conv(sd, "Chain.Conv2d", h, padding=1)
+
+
+# -------------------------------------------------------------------------------------- SDXL
+# (cout, attention layers, heads) per level entry; None marks Downsample
+_SDXL_DOWN = [("in",), ("res", 0, 0), ("res", 0, 0), ("down",), ("res", 2, 10), ("res", 2, 10), ("down",),
+              ("res", 10, 20), ("res", 10, 20)]
+_SDXL_UP = [(10, 20, False), (10, 20, False), (10, 20, True), (2, 10, False), (2, 10, False), (2, 10, True),
+            (0, 0, False), (0, 0, False), (0, 0, False)]
+
+
+def sdxl_timestep_embedding(sd: SD, timestep: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor, dtype: torch.dtype) -> Tensor:
+    """TimestepEncoder (sdxl/unet.py:62-90) = RangeEncoder(timestep) + TextTimeEmbedding (:20-59):
+    MLP(cat(pooled[B,1280], sinusoid256(time_ids[B,6]) flattened to [B,1536]))."""
+    t = range_encoder(sd, "TimestepEncoder.Sum.Chain.RangeEncoder", timestep, dtype)
+    ids = ops.sinusoidal_embedding(time_ids.unsqueeze(-1), 256)  # [B, 1, 6, 256]
+    ids = ids.reshape(ids.shape[0], -1)
+    tt = torch.cat([pooled_text_embedding, ids], dim=1).to(dtype)
+    p = "TimestepEncoder.Sum.TextTimeEmbedding"
+    tt = _lin(sd, p + ".Linear_2", ops.silu(_lin(sd, p + ".Linear_1", tt)))
+    return t + tt
+
+
+def sdxl_unet(
+    sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor
+) -> Tensor:
+    """SDXLUNet forward (sdxl/unet.py:258-351)."""
+    dtype = x.dtype
+    temb = sdxl_timestep_embedding(sd, timestep, pooled_text_embedding, time_ids, dtype)
+    skips: list[Tensor] = []
+    h = x
+    for i, entry in enumerate(_SDXL_DOWN):
+        p = f"DownBlocks.Chain_{i + 1}"
+        if entry[0] == "in":
+            h = _conv(sd, p + ".Conv2d", h, padding=1)
+        elif entry[0] == "down":
+            h = _conv(sd, p + ".Downsample.Conv2d", h, stride=2, padding=1)
+        else:
+            h = residual_block(sd, p + ".ResidualBlock", h, temb)
+            if entry[1]:
+                h = cross_attention_2d(sd, p + ".SDXLCrossAttention", h, clip_text_embedding, entry[2], entry[1], True)
+        skips.append(h)
+    m = "MiddleBlock"
+    h = residual_block(sd, m + ".ResidualBlock_1", h, temb)
+    h = cross_attention_2d(sd, m + ".SDXLCrossAttention", h, clip_text_embedding, 20, 10, True)
+    h = residual_block(sd, m + ".ResidualBlock_2", h, temb)
+    h = h + 0.0  # Residual(UseContext residuals[-1]): the spare 10th slot keeps its initial 0.0
+    for n, (layers, heads, up) in enumerate(_SDXL_UP):
+        p = f"UpBlocks.Chain_{n + 1}"
+        h = torch.cat([h, skips[-n - 1]], dim=1)  # ResidualConcatenator(-n-2) on a list with one spare slot
+        h = residual_block(sd, p + ".ResidualBlock", h, temb)
+        if layers:
+            h = cross_attention_2d(sd, p + ".SDXLCrossAttention", h, clip_text_embedding, heads, layers, True)
+        if up:
+            h = ops.nearest_upsample(h, (h.shape[-2] * 2, h.shape[-1] * 2))
+            h = _conv(sd, p + ".Upsample.Conv2d", h, padding=1)
+    h = ops.silu(ops.group_norm(h, 32, sd["OutputBlock.GroupNorm.weight"], sd["OutputBlock.GroupNorm.bias"], 1e-5))
+    return _conv(sd, "OutputBlock.Conv2d", h, padding=1)

@@ -2,7 +2,7 @@
 
 import torch
 
-EPS = {torch.bfloat16: 2.0**-8, torch.float16: 2.0**-11, torch.float32: 2.0**-20}
+EPS = {torch.bfloat16: 2.0**-8, torch.float16: 2.0**-11, torch.float32: 2.0**-16}
 
 
 def rounded(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
