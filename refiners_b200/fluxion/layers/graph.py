@@ -36,6 +36,11 @@ def structure_epoch() -> int:
     return _structure_epoch
 
 
+# observers of Chain.set_context (refiners_b200.engine.graph mirrors context tensors into the
+# static buffers of a captured CUDA graph); a listener returning True has consumed the update
+_context_listeners: list[Callable[["Chain", str, Any], bool]] = []
+
+
 def generate_unique_names(modules: Sequence[Module]) -> dict[str, Module]:
     """``ClassName`` when the class appears once among the siblings, else ``ClassName_<i>``
     (1-based, in order).  These names are the state-dict keys."""
@@ -132,6 +137,9 @@ class Chain(ContextModule):
         self._register_provider(self.init_context())
 
     def set_context(self, context: str, value: Any) -> None:
+        for listener in _context_listeners:
+            if listener(self, context, value):
+                return
         self._provider.set_context(context, value)
         self._register_provider()
 

@@ -43,6 +43,24 @@ class LatentDiffusionModel(fl.Module, ABC):
         )
         self.solver = solver.to(device=self.device, dtype=self.dtype)
         self.classifier_free_guidance = classifier_free_guidance
+        self._graphed_unet: list[object] = []  # list-wrapped: not a torch sub-module
+
+    def enable_cuda_graph(self, enabled: bool = True) -> None:
+        """Replay the UNet forward from a captured CUDA graph (refiners_b200.engine.graph).
+        The first call after enabling - or after any structural edit - runs the Python walker
+        once under capture; contexts keep being set through the normal API."""
+        for runner in self._graphed_unet:
+            runner.close()  # type: ignore[attr-defined]
+        self._graphed_unet = []
+        if enabled:
+            from refiners_b200.engine.graph import GraphedChain
+
+            self._graphed_unet = [GraphedChain(self.unet)]
+
+    def _run_unet(self, latents: Tensor) -> Tensor:
+        if self._graphed_unet and latents.is_cuda:
+            return self._graphed_unet[0](latents)  # type: ignore[operator]
+        return self.unet(latents)
 
     def set_inference_steps(self, num_steps: int, first_step: int = 0) -> None:
         self.solver = self.solver.rebuild(num_inference_steps=num_steps, first_inference_step=first_step)
@@ -99,7 +117,7 @@ class LatentDiffusionModel(fl.Module, ABC):
         latents = torch.cat((x, x)) if cfg else x
         latents = self.solver.scale_model_input(latents, step=step)
         if cfg:
-            unconditional, conditional = self.unet(latents).chunk(2)
+            unconditional, conditional = self._run_unet(latents).chunk(2)
             predicted_noise = unconditional + condition_scale * (conditional - unconditional)
             x = x.narrow(dim=1, start=0, length=4)  # > 4 input channels (inpainting) keep 4 latent ones
             if self.has_self_attention_guidance():
@@ -107,7 +125,7 @@ class LatentDiffusionModel(fl.Module, ABC):
                     x=x, noise=unconditional, step=step, clip_text_embedding=clip_text_embedding, **kwargs
                 )
         else:
-            predicted_noise = self.unet(latents)
+            predicted_noise = self._run_unet(latents)
             x = x.narrow(dim=1, start=0, length=4)
         return self.solver(x, predicted_noise=predicted_noise, step=step)
 
