@@ -114,6 +114,8 @@ struct SdpaProblem {
   int64_t q_sb, q_ss, k_sb, k_ss, v_sb, v_ss, o_sb, o_ss;
   float scale; int causal;
   const void *k2, *v2; int64_t Sk2, k2_sb, k2_ss, v2_sb, v2_ss; float scale2;
+  // optional decomposed relative-position bias (SAM): logits[q, kh * bias_W + kw] += bias_h[b, h, q, kh] + bias_w[b, h, q, kw]
+  const float *bias_h, *bias_w; int bias_H, bias_W;
 };
 int simt_sdpa(cudaStream_t st, const SdpaProblem& p);
 bool tc_sdpa_supported(const SdpaProblem& p);

@@ -1,7 +1,506 @@
-// tcgen05 flash attention (placeholder dispatch until the kernel lands in this file).
+// tcgen05 flash attention for sm_100a: head dim 64, bf16/fp16, non-causal.
+//
+//   O[b, q, h, :] = softmax(Q K^T * scale) V  (+ scale2 * softmax(Q K2^T * scale) V2)
+//
+// One CTA owns a 128-query tile of one (batch, head) at a time (persistent, two CTAs per SM so
+// that one CTA's softmax overlaps the other's MMAs).  Per 64-key tile:
+//   warp 0      TMA: K and V tiles [64 keys x 64] -> 128B-swizzled smem ring (3 stages); Q tile once
+//   warp 1      one thread issues  S = Q K^T  (UMMA 128x64x16, SS, K-major B)  -> TMEM S
+//                                  O_j = P V   (UMMA 128x64x16, SS, MN-major B) -> TMEM O
+//   warps 2..5  softmax: thread = query row (TMEM lane): tcgen05.ld S, online max / exp2 / sum in
+//               fp32, P -> bf16 -> swizzled smem (the A operand of the second MMA), and the running
+//               output is kept in registers: O = O * alpha + O_j (tcgen05.ld of the 64-col O_j).
+// The [B, S, H*D] operands are addressed in place through 4D tensor maps (D, H, S, B): the head
+// split/merge of the reference (fluxion/layers/attentions.py:177-202) costs no copies.
+// The Sq x Sk score matrix never exists in memory.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace rb200 {
-bool tc_sdpa_supported(const SdpaProblem&) { return false; }
-int tc_sdpa(cudaStream_t, const SdpaProblem&) { RB200_FAIL(-5, "tc_sdpa: not built"); }
+namespace {
+
+constexpr int QT = 128;   // queries per tile (UMMA M)
+constexpr int KT = 64;    // keys per tile
+constexpr int HD = 64;    // head dim
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 192;
+constexpr int Q_BYTES = QT * HD * 2, K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2, P_BYTES = QT * KT * 2;
+constexpr int TMEM_COLS = 128;  // S: cols [0, 64), O: cols [64, 128)
+constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+
+struct AttnParams {
+  void* o;
+  int64_t o_sb, o_ss;
+  int64_t B;
+  int H;
+  int64_t Sq, Sk, Sk2;
+  int n_qt;
+  int64_t total_work;
+  float scale_log2e;
+  float scale2;
+  uint32_t idesc_qk, idesc_pv;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 26)) __trap();  // protocol bug: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SW128 tile (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {
+  return uint64_t((addr >> 4) & 0x3FFF) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// MN-major SW128 tile [K rows][64 MN elements]: 8-row K groups are 1024 B apart (SBO); a single
+// 64-element atom along MN, so the leading offset is unused (set to the tile size)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t tile_bytes) {
+  return uint64_t((addr >> 4) & 0x3FFF) | (uint64_t((tile_bytes >> 4) & 0x3FFF) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T, bool DUAL>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+               const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
+               const __grid_constant__ CUtensorMap map_v2, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + STAGES * K_BYTES;
+  uint8_t* sP = sV + STAGES * V_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* kv_full = bars;              // [STAGES]
+  uint64_t* kv_empty = bars + STAGES;    // [STAGES]
+  uint64_t* q_full = bars + 2 * STAGES;
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* bar_s = q_full + 2;          // S tile ready in TMEM
+  uint64_t* bar_p = q_full + 3;          // P tile written to smem (S and previous O consumed)
+  uint64_t* bar_o = q_full + 4;          // O_j ready in TMEM (P and V slot consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsets = DUAL ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_k);
+    prefetch_tmap(&map_v);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 4);
+    mbar_init(bar_o, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+
+  if (warp == 0) {
+    // ================================================================================ TMA
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int qt = int(w % p.n_qt);
+        const int h = int((w / p.n_qt) % p.H);
+        const int b = int(w / (int64_t(p.n_qt) * p.H));
+        mbar_wait(q_empty, qphase ^ 1);
+        mbar_arrive_expect_tx(q_full, Q_BYTES);
+        tma_load_4d(sQ, &map_q, q_full, 0, h, qt * QT, b);
+        qphase ^= 1;
+        for (int set = 0; set < nsets; ++set) {
+          const int64_t Sk = set ? p.Sk2 : p.Sk;
+          const int ntiles = int((Sk + KT - 1) / KT);
+          for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(&kv_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
+            tma_load_4d(sK + stage * K_BYTES, set ? &map_k2 : &map_k, &kv_full[stage], 0, h, j * KT, b);
+            tma_load_4d(sV + stage * V_BYTES, set ? &map_v2 : &map_v, &kv_full[stage], 0, h, j * KT, b);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================================ MMA
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0, pphase = 0;
+      const uint64_t dq = desc_kmajor(smem_u32(sQ));
+      const uint64_t dp = desc_kmajor(smem_u32(sP));
+      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        mbar_wait(q_full, qphase);
+        qphase ^= 1;
+        tcgen05_fence_after();
+        for (int set = 0; set < nsets; ++set) {
+          const int64_t Sk = set ? p.Sk2 : p.Sk;
+          const int ntiles = int((Sk + KT - 1) / KT);
+          // S_0 = Q K_0^T
+          mbar_wait(&kv_full[stage], phase);
+          tcgen05_fence_after();
+          {
+            const uint64_t dk = desc_kmajor(smem_u32(sK + stage * K_BYTES));
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+          }
+          umma_commit(bar_s);
+          for (int j = 0; j < ntiles; ++j) {
+            // P_j is in smem, S_j and O_{j-1} have been read by the softmax warps
+            mbar_wait(bar_p, pphase);
+            pphase ^= 1;
+            tcgen05_fence_after();
+            const uint64_t dv = desc_mnmajor(smem_u32(sV + stage * V_BYTES), V_BYTES);
+#pragma unroll
+            for (int k = 0; k < KT / 16; ++k) {
+              // A: +32 B per 16 keys inside the swizzle atom; B (MN-major): +16 rows * 128 B
+              umma_f16(tmem_o, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
+            }
+            umma_commit(&kv_empty[stage]);  // K_j / V_j slot free once these MMAs retire
+            umma_commit(bar_o);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (j + 1 < ntiles) {
+              mbar_wait(&kv_full[stage], phase);
+              tcgen05_fence_after();
+              const uint64_t dk = desc_kmajor(smem_u32(sK + stage * K_BYTES));
+#pragma unroll
+              for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+              umma_commit(bar_s);
+            }
+          }
+        }
+        umma_commit(q_empty);  // every MMA reading Q has been issued; the slot frees when they retire
+      }
+    }
+  } else {
+    // ============================================================================ softmax
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const uint32_t lane_off = uint32_t(lg * 32) << 16;
+    uint32_t sphase = 0, ophase = 0;
+    uint8_t* prow = sP + row * 128;
+    const int sw = row & 7;
+    T* obase = static_cast<T*>(p.o);
+    for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int qt = int(w % p.n_qt);
+      const int h = int((w / p.n_qt) % p.H);
+      const int64_t b = w / (int64_t(p.n_qt) * p.H);
+      float out[DUAL ? HD : 1];
+      if constexpr (DUAL) {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) out[i] = 0.f;
+      }
+      float acc[HD];
+      for (int set = 0; set < nsets; ++set) {
+        const int64_t Sk = set ? p.Sk2 : p.Sk;
+        const int ntiles = int((Sk + KT - 1) / KT);
+#pragma unroll
+        for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < ntiles; ++j) {
+          mbar_wait(bar_s, sphase);
+          sphase ^= 1;
+          tcgen05_fence_after();
+          float s[KT];
+          {
+            uint32_t raw0[32], raw1[32];
+            tmem_ld_32x32(tmem_s + lane_off, raw0);
+            tmem_ld_32x32(tmem_s + lane_off + 32, raw1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              s[i] = __uint_as_float(raw0[i]);
+              s[32 + i] = __uint_as_float(raw1[i]);
+            }
+          }
+          const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT);
+          if (valid < KT) {
+#pragma unroll
+            for (int i = 0; i < KT; ++i)
+              if (i >= valid) s[i] = -INFINITY;
+          }
+          float tmax = s[0];
+#pragma unroll
+          for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
+          const float m_new = fmaxf(m_run, tmax);
+          const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // exp2(-inf) = 0 on the first tile
+          const float mb = m_new * p.scale_log2e;
+          float psum = 0.f;
+          uint32_t packed[KT / 2];
+#pragma unroll
+          for (int i = 0; i < KT; i += 2) {
+            const float p0 = fast_exp2(fmaf(s[i], p.scale_log2e, -mb));
+            const float p1 = fast_exp2(fmaf(s[i + 1], p.scale_log2e, -mb));
+            psum += p0 + p1;
+            packed[i / 2] = pack2<T>(p0, p1);
+          }
+          l_run = l_run * alpha + psum;
+          m_run = m_new;
+          if (j > 0) {
+            // O_{j-1} = P_{j-1} V_{j-1} has landed: fold it in, then rescale to the new maximum
+            mbar_wait(bar_o, ophase);
+            ophase ^= 1;
+            tcgen05_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t raw[32];
+              tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[half * 32 + i] = (acc[half * 32 + i] + __uint_as_float(raw[i])) * alpha;
+            }
+          }
+          // P_j -> smem, K-major with the 128B swizzle the MMA descriptor expects
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 v = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
+            *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = v;
+          }
+          fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_p);
+        }
+        // last tile of the set
+        mbar_wait(bar_o, ophase);
+        ophase ^= 1;
+        tcgen05_fence_after();
+        {
+          const float wgt = (set ? p.scale2 : 1.f) * (l_run > 0.f ? 1.f / l_run : 0.f);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = wgt * (acc[half * 32 + i] + __uint_as_float(raw[i]));
+              if constexpr (DUAL) out[half * 32 + i] += v;
+              else acc[half * 32 + i] = v;
+            }
+          }
+        }
+        // the next set (or work item) reuses the O accumulator in TMEM only after a new P tile is
+        // published, which happens after these loads - no extra fence needed here
+      }
+      float* fin = DUAL ? out : acc;
+      const int64_t qi = int64_t(qt) * QT + row;
+      if (qi < p.Sq) {
+        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * HD;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 v;
+            v.x = pack2<T>(fin[c * 8], fin[c * 8 + 1]);
+            v.y = pack2<T>(fin[c * 8 + 2], fin[c * 8 + 3]);
+            v.z = pack2<T>(fin[c * 8 + 4], fin[c * 8 + 5]);
+            v.w = pack2<T>(fin[c * 8 + 6], fin[c * 8 + 7]);
+            reinterpret_cast<uint4*>(dst)[c] = v;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < HD; ++i) dst[i] = from_f<T>(fin[i]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return EncodeTiledFn(nullptr);
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+
+// [B, S, H, D] view with strides (sb, ss, D, 1) elements; box = D x 1 x rows x 1
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t B, int64_t S, int H, int64_t sb, int64_t ss, int rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) RB200_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t dims[4] = {cuuint64_t(HD), cuuint64_t(H), cuuint64_t(S), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(HD) * 2, cuuint64_t(ss) * 2, cuuint64_t(sb) * 2};
+  const cuuint32_t box[4] = {HD, 1, cuuint32_t(rows), 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == RB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult rc = fn(map, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) RB200_FAIL(-4, "sdpa tensor map encode failed (%d): S=%lld H=%d ss=%lld sb=%lld", int(rc), (long long)S, H, (long long)ss, (long long)sb);
+  return 0;
+}
+
+bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
+}
+
+template <typename T, bool DUAL>
+int launch(cudaStream_t st, const SdpaProblem& s, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+           const CUtensorMap& mk2, const CUtensorMap& mv2, const AttnParams& prm) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+    configured = true;
+  }
+  const int64_t cap = int64_t(sm_count()) * 2;
+  const int grid = int(prm.total_work < cap ? prm.total_work : cap);
+  tc_sdpa_kernel<T, DUAL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk, mv, mk2, mv2, prm);
+  RB200_CHECK_LAUNCH("tc_sdpa");
+  (void)s;
+  return 0;
+}
+
+}  // namespace
+
+bool tc_sdpa_supported(const SdpaProblem& p) {
+  if (p.dtype != RB200_BF16 && p.dtype != RB200_FP16) return false;
+  if (p.D != HD || p.causal || p.bias_h != nullptr) return false;
+  if (p.Sq < 1 || p.Sk < 1 || p.B < 1) return false;
+  if (!ok_operand(p.q, p.q_sb, p.q_ss) || !ok_operand(p.k, p.k_sb, p.k_ss) || !ok_operand(p.v, p.v_sb, p.v_ss)) return false;
+  if (p.k2 && p.Sk2 > 0 && (!ok_operand(p.k2, p.k2_sb, p.k2_ss) || !ok_operand(p.v2, p.v2_sb, p.v2_ss))) return false;
+  // tiny problems are launch-bound either way; keep them on the simple kernel
+  return true;
+}
+
+int tc_sdpa(cudaStream_t st, const SdpaProblem& p) {
+  CUtensorMap mq, mk, mv, mk2, mv2;
+  if (int rc = make_map(&mq, p.dtype, p.q, p.B, p.Sq, p.H, p.q_sb, p.q_ss, QT)) return rc;
+  if (int rc = make_map(&mk, p.dtype, p.k, p.B, p.Sk, p.H, p.k_sb, p.k_ss, KT)) return rc;
+  if (int rc = make_map(&mv, p.dtype, p.v, p.B, p.Sk, p.H, p.v_sb, p.v_ss, KT)) return rc;
+  const bool dual = p.k2 != nullptr && p.Sk2 > 0;
+  if (dual) {
+    if (int rc = make_map(&mk2, p.dtype, p.k2, p.B, p.Sk2, p.H, p.k2_sb, p.k2_ss, KT)) return rc;
+    if (int rc = make_map(&mv2, p.dtype, p.v2, p.B, p.Sk2, p.H, p.v2_sb, p.v2_ss, KT)) return rc;
+  } else {
+    mk2 = mk;
+    mv2 = mv;
+  }
+  AttnParams prm{};
+  prm.o = p.o;
+  prm.o_sb = p.o_sb;
+  prm.o_ss = p.o_ss;
+  prm.B = p.B;
+  prm.H = p.H;
+  prm.Sq = p.Sq;
+  prm.Sk = p.Sk;
+  prm.Sk2 = dual ? p.Sk2 : 0;
+  prm.n_qt = int(ceil_div(p.Sq, QT));
+  prm.total_work = int64_t(prm.n_qt) * p.H * p.B;
+  prm.scale_log2e = p.scale * 1.4426950408889634f;
+  prm.scale2 = p.scale2;
+  const uint32_t fmt = p.dtype == RB200_BF16 ? 1u : 0u;
+  const uint32_t common = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(QT >> 4) << 24);
+  prm.idesc_qk = common;               // A, B K-major
+  prm.idesc_pv = common | (1u << 16);  // B (= V) MN-major
+  if (p.dtype == RB200_BF16)
+    return dual ? launch<__nv_bfloat16, true>(st, p, mq, mk, mv, mk2, mv2, prm) : launch<__nv_bfloat16, false>(st, p, mq, mk, mv, mk2, mv2, prm);
+  return dual ? launch<__half, true>(st, p, mq, mk, mv, mk2, mv2, prm) : launch<__half, false>(st, p, mq, mk, mv, mk2, mv2, prm);
+}
+
 }  // namespace rb200

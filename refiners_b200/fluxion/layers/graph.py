@@ -150,11 +150,36 @@ class Chain(ContextModule):
         except Exception as exc:
             raise ChainError(self._describe_failure(exc, name, args)) from None
 
+    def _call_fused(self, name: str, fn: Callable[..., Any], /, *args: Any) -> Any:
+        """Run a fused kernel standing in for the child ``name`` (+ its successor) with the same
+        error reporting as a plain child call."""
+        try:
+            return fn(*args)
+        except Exception as exc:
+            raise ChainError(self._describe_failure(exc, name, args)) from None
+
+    def _steps(self) -> list[tuple[Any, ...]]:
+        """Cached fusion plan over the current children (dropped by every structural edit)."""
+        if self._plan is None:
+            from refiners_b200.engine.fusion import build_plan
+
+            self._plan = build_plan(self)
+        return self._plan
+
+    def _run_children(self, args: tuple[Any, ...], skip_last: bool = False) -> Any:
+        """Walk the children (through the fusion plan); optionally stop before the last child and
+        return the arguments it would receive."""
+        from refiners_b200.engine.fusion import run_steps
+
+        steps = self._steps()
+        if skip_last:
+            assert steps and steps[-1][0] == "call"
+            result = run_steps(self, steps[:-1], args) if len(steps) > 1 else (args[0] if len(args) == 1 else args)
+            return result
+        return run_steps(self, steps, args)
+
     def forward(self, *args: Any) -> Any:
-        result: Any = None
-        for name, layer in self._modules.items():
-            result = self._call_layer(layer, name, *args)
-            args = result if isinstance(result, tuple) else (result,)
+        result = self._run_children(args)
         self._reset_context()
         return result
 
@@ -481,12 +506,26 @@ class Sum(Chain):
     _tag = "SUM"
 
     def forward(self, *inputs: Any) -> Any:
+        on_gpu = bool(inputs) and isinstance(inputs[0], Tensor) and inputs[0].is_cuda
+        if on_gpu:
+            from refiners_b200.engine import fusion
+
+            fused = fusion.try_fuse_sum(self, inputs)
+            if fused is not NotImplemented:
+                return fused
         total: Any = None
         for layer in self._modules.values():
             term = layer(*inputs)
             if isinstance(term, tuple):
                 term = sum(term)
-            total = term if total is None else total + term
+            if total is None:
+                total = term
+            elif on_gpu and isinstance(term, Tensor) and isinstance(total, Tensor) and term.shape == total.shape and term.dtype == total.dtype:
+                from refiners_b200 import backend as B
+
+                total = B.add(total, term)
+            else:
+                total = total + term
         return total
 
     def _show_only_tag(self) -> bool:
@@ -498,7 +537,28 @@ class Residual(Chain):
 
     def forward(self, *inputs: Any) -> Any:
         assert len(inputs) == 1, "Residual connection can only be used with a single input."
-        return Chain.forward(self, *inputs) + inputs[0]
+        x = inputs[0]
+        if isinstance(x, Tensor) and x.is_cuda:
+            from refiners_b200 import backend as B
+            from refiners_b200.engine import fusion
+
+            last = fusion.tail_linear(self) if B.fusion_enabled() else None
+            if last is not None and self._steps()[-1][0] == "call":
+                # the final GEMM adds the skip connection in its epilogue (fp32, one launch)
+                h = self._run_children(inputs, skip_last=True)
+                if isinstance(h, Tensor) and h.shape[:-1] == x.shape[:-1] and last.out_features == x.shape[-1]:
+                    name = next(reversed(self._modules))
+                    out = self._call_fused(name, lambda t: B.linear(t, last.weight, last.bias, residual=x), h)
+                    self._reset_context()
+                    return out
+                out = self._call_layer(last, next(reversed(self._modules)), *(h if isinstance(h, tuple) else (h,)))
+                self._reset_context()
+                return B.add(out, x) if out.shape == x.shape and out.dtype == x.dtype else out + x
+            out = Chain.forward(self, *inputs)
+            if isinstance(out, Tensor) and out.shape == x.shape and out.dtype == x.dtype and out.is_cuda:
+                return B.add(out, x)
+            return out + x
+        return Chain.forward(self, *inputs) + x
 
 
 class Concatenate(Chain):

@@ -1,0 +1,272 @@
+"""IP-Adapter: image-prompt conditioning injected into every text cross-attention.
+
+Per-step behaviour follows /root/reference/src/refiners/foundationals/latent_diffusion/image_prompt.py:
+`ImageProjection` :24-45, `ImageCrossAttention` :237-278, `CrossAttentionAdapter` :281-347,
+`IPAdapter` :350-455, and stable_diffusion_xl/image_prompt.py:9-65 (`SDXLIPAdapter`).
+
+Scope: the CLIP image encoder and the fine-grained PerceiverResampler run once per prompt, outside
+the denoising loop - they are optional constructor arguments here and
+the benchmarks feed a synthetic ``clip_image_embedding`` through ``set_clip_image_embedding``.
+
+B200 addition: after injection each cross-attention contains ``Sum(SDPA, ImageCrossAttention)``;
+on CUDA that Sum runs as ONE flash-attention launch with two key/value sets and two independent
+softmaxes (``o = A(q,k_t,v_t) + s * A(q,k_i,v_i)``) - registered below as a Sum fuser, the tree is
+untouched.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Generic, TypeVar
+
+import torch
+from torch import Tensor, nn
+
+import refiners_b200.fluxion.layers as fl
+from refiners_b200 import backend as B
+from refiners_b200.engine import fusion
+from refiners_b200.fluxion.adapters.adapter import Adapter
+from refiners_b200.fluxion.layers.leaves import ScaledDotProductAttention
+from refiners_b200.foundationals.latent_diffusion.cross_attention import CrossAttentionBlock2d
+
+T = TypeVar("T", bound=fl.Chain)
+TIPAdapter = TypeVar("TIPAdapter", bound="IPAdapter[Any]")
+Device = torch.device
+DType = torch.dtype
+
+
+class ImageProjection(fl.Chain):
+    """CLIP image embedding [B, E] -> ``num_tokens`` text-space tokens [B, T, C]."""
+
+    def __init__(
+        self,
+        clip_image_embedding_dim: int = 1024,
+        clip_text_embedding_dim: int = 768,
+        num_tokens: int = 4,
+        device: Device | str | None = None,
+        dtype: DType | None = None,
+    ) -> None:
+        self.clip_image_embedding_dim = clip_image_embedding_dim
+        self.clip_text_embedding_dim = clip_text_embedding_dim
+        self.num_tokens = num_tokens
+        super().__init__(
+            fl.Linear(clip_image_embedding_dim, clip_text_embedding_dim * num_tokens, device=device, dtype=dtype),
+            fl.Reshape(num_tokens, clip_text_embedding_dim),
+            fl.LayerNorm(normalized_shape=clip_text_embedding_dim, device=device, dtype=dtype),
+        )
+
+
+class ImageCrossAttention(fl.Chain):
+    """(q, k_text, v_text) -> scale * SDPA(q, Wk' e, Wv' e) with e = ``ip_adapter.clip_image_embedding``."""
+
+    def __init__(self, text_cross_attention: fl.Attention, scale: float = 1.0) -> None:
+        self._multiply = [fl.Multiply(scale)]
+        tca = text_cross_attention
+        kw = dict(bias=tca.use_bias, device=tca.device, dtype=tca.dtype)
+        super().__init__(
+            fl.Distribute(
+                fl.Identity(),
+                fl.Chain(
+                    fl.UseContext(context="ip_adapter", key="clip_image_embedding"),
+                    fl.Linear(tca.key_embedding_dim, tca.inner_dim, **kw),
+                ),
+                fl.Chain(
+                    fl.UseContext(context="ip_adapter", key="clip_image_embedding"),
+                    fl.Linear(tca.value_embedding_dim, tca.inner_dim, **kw),
+                ),
+            ),
+            ScaledDotProductAttention(num_heads=tca.num_heads, is_causal=tca.is_causal),
+            self.multiply,
+        )
+
+    @property
+    def multiply(self) -> fl.Multiply:
+        return self._multiply[0]
+
+    @property
+    def scale(self) -> float:
+        return self.multiply.scale
+
+    @scale.setter
+    def scale(self, value: float) -> None:
+        self.multiply.scale = value
+
+
+class CrossAttentionAdapter(fl.Chain, Adapter[fl.Attention]):
+    def __init__(self, target: fl.Attention, scale: float = 1.0) -> None:
+        with self.setup_adapter(target):
+            super().__init__(target)
+        self._image_cross_attention = [ImageCrossAttention(text_cross_attention=target, scale=scale)]
+
+    def inject(self, parent: fl.Chain | None = None) -> "CrossAttentionAdapter":
+        sdpa = self.target.ensure_find(ScaledDotProductAttention)
+        # the text SDPA becomes Sum(text SDPA, image cross-attention)
+        self.target.replace(old_module=sdpa, new_module=fl.Sum(sdpa, self.image_cross_attention))
+        return super().inject(parent)
+
+    def eject(self) -> None:
+        holder = self.target.ensure_find_parent(self.image_cross_attention)
+        holder.remove(self.image_cross_attention)
+        sdpa = holder.layer("ScaledDotProductAttention", ScaledDotProductAttention)
+        self.target.replace(old_module=holder, new_module=sdpa)
+        super().eject()
+
+    @property
+    def image_cross_attention(self) -> ImageCrossAttention:
+        return self._image_cross_attention[0]
+
+    @property
+    def image_key_projection(self) -> fl.Linear:
+        return self.image_cross_attention.layer(("Distribute", 1, "Linear"), fl.Linear)
+
+    @property
+    def image_value_projection(self) -> fl.Linear:
+        return self.image_cross_attention.layer(("Distribute", 2, "Linear"), fl.Linear)
+
+    @property
+    def scale(self) -> float:
+        return self.image_cross_attention.scale
+
+    @scale.setter
+    def scale(self, value: float) -> None:
+        self.image_cross_attention.scale = value
+
+    def load_weights(self, key_tensor: Tensor, value_tensor: Tensor) -> None:
+        self.image_key_projection.weight = nn.Parameter(key_tensor)
+        self.image_value_projection.weight = nn.Parameter(value_tensor)
+        self.image_cross_attention.to(self.device, self.dtype)
+
+
+class IPAdapter(Generic[T], fl.Chain, Adapter[T]):
+    """Image-prompt adapter for a latent-diffusion UNet: one `CrossAttentionAdapter` per text
+    cross-attention (70 in SDXL)."""
+
+    def __init__(
+        self,
+        target: T,
+        clip_image_encoder: fl.Chain | None,
+        image_proj: fl.Module | None,
+        scale: float = 1.0,
+        fine_grained: bool = False,
+        weights: dict[str, Tensor] | None = None,
+    ) -> None:
+        with self.setup_adapter(target):
+            super().__init__(target)
+        self.fine_grained = fine_grained
+        # list-wrapped: these are not part of the UNet's state dict
+        self._clip_image_encoder = [clip_image_encoder]
+        self._image_proj = [image_proj]
+        self.sub_adapters = [
+            CrossAttentionAdapter(target=attn, scale=scale)
+            for attn in target.layers(fl.Attention)
+            if type(attn) is not fl.SelfAttention
+        ]
+        if weights is not None:
+            if image_proj is not None:
+                image_proj.load_state_dict(
+                    {k.removeprefix("image_proj."): v for k, v in weights.items() if k.startswith("image_proj.")}
+                )
+            for i, sub in enumerate(self.sub_adapters):
+                pair = [v for k, v in weights.items() if k.startswith(f"ip_adapter.{i:03d}.")]
+                assert len(pair) == 2
+                sub.load_weights(*pair)
+
+    @property
+    def clip_image_encoder(self) -> fl.Chain:
+        enc = self._clip_image_encoder[0]
+        assert enc is not None, "no CLIP image encoder attached (it runs outside the denoising loop)"
+        return enc
+
+    @property
+    def image_proj(self) -> fl.Module:
+        proj = self._image_proj[0]
+        assert proj is not None, "no image projection attached"
+        return proj
+
+    def inject(self: TIPAdapter, parent: fl.Chain | None = None) -> TIPAdapter:
+        for sub in self.sub_adapters:
+            sub.inject()
+        return super().inject(parent)
+
+    def eject(self) -> None:
+        for sub in self.sub_adapters:
+            sub.eject()
+        super().eject()
+
+    @property
+    def scale(self) -> float:
+        return self.sub_adapters[0].scale
+
+    @scale.setter
+    def scale(self, value: float) -> None:
+        for sub in self.sub_adapters:
+            sub.scale = value
+
+    def set_clip_image_embedding(self, image_embedding: Tensor) -> None:
+        """[B, T, C] image tokens read by every `ImageCrossAttention` (T = 4, or 16 fine-grained)."""
+        self.set_context("ip_adapter", {"clip_image_embedding": image_embedding})
+
+    def project_image_embedding(self, clip_embedding: Tensor, negative: Tensor | None = None) -> Tensor:
+        """image_proj(clip embedding), with the unconditional half first when given
+        (reference image_prompt.py:457-511, minus the encoder call)."""
+        cond = self.image_proj(clip_embedding)
+        if negative is None:
+            return cond
+        return torch.cat((self.image_proj(negative), cond))
+
+
+class SDXLIPAdapter(IPAdapter[fl.Chain]):
+    def __init__(
+        self,
+        target: fl.Chain,
+        clip_image_encoder: fl.Chain | None = None,
+        image_proj: fl.Module | None = None,
+        scale: float = 1.0,
+        fine_grained: bool = False,
+        weights: dict[str, Tensor] | None = None,
+        clip_image_embedding_dim: int = 1024,
+    ) -> None:
+        if image_proj is None and not fine_grained:
+            xattn = target.ensure_find(CrossAttentionBlock2d)
+            image_proj = ImageProjection(
+                clip_image_embedding_dim=clip_image_embedding_dim,
+                clip_text_embedding_dim=xattn.context_embedding_dim,
+                device=target.device,
+                dtype=target.dtype,
+            )
+        super().__init__(
+            target=target,
+            clip_image_encoder=clip_image_encoder,
+            image_proj=image_proj,
+            scale=scale,
+            fine_grained=fine_grained,
+            weights=weights,
+        )
+
+
+# --------------------------------------------------------------------------- fused execution
+def _fuse_text_image_attention(chain: fl.Sum, inputs: tuple[Any, ...]) -> Any:
+    """Sum(SDPA, ImageCrossAttention)(q, k, v) as one dual-KV attention launch."""
+    if len(chain) != 2 or len(inputs) != 3:
+        return NotImplemented
+    sdpa, ica = chain[0], chain[1]
+    if type(sdpa) is not ScaledDotProductAttention or type(ica) is not ImageCrossAttention:
+        return NotImplemented
+    q, k, v = inputs
+    if not (isinstance(q, Tensor) and q.is_cuda) or sdpa.is_causal or sdpa.slice_size:
+        return NotImplemented
+    kids = list(ica)
+    if len(kids) != 3 or type(kids[0]) is not fl.Distribute or type(kids[1]) is not ScaledDotProductAttention:
+        return NotImplemented
+    if type(kids[2]) is not fl.Multiply or kids[2].bias != 0.0 or kids[1].num_heads != sdpa.num_heads or kids[1].is_causal:
+        return NotImplemented
+    dist = kids[0]
+    if len(dist) != 3 or type(dist[0]) is not fl.Identity:
+        return NotImplemented
+    if fusion._hooked(sdpa, ica, kids[1], kids[2]):
+        return NotImplemented
+    k2 = dist[1](k)   # Chain(UseContext, Linear): ignores its input, projects the image tokens
+    v2 = dist[2](v)
+    return B.sdpa(q, k, v, sdpa.num_heads, False, k2=k2, v2=v2, scale2=float(kids[2].scale))
+
+
+fusion.register_sum_fuser(_fuse_text_image_attention)

@@ -6,10 +6,14 @@ Tree shapes follow /root/reference/src/refiners/foundationals/latent_diffusion/u
 
 from __future__ import annotations
 
+from typing import Any
+
 import torch
 from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
+from refiners_b200 import backend as B
+from refiners_b200.engine import fusion
 
 Device = torch.device
 DType = torch.dtype
@@ -46,6 +50,25 @@ class ResidualBlock(fl.Sum):
             fl.Conv2d(out_channels, out_channels, kernel_size=3, padding=1, **kw),
         )
         super().__init__(body, shortcut)
+
+    def forward(self, *inputs: Any) -> Any:
+        """Sum(body, shortcut).  On CUDA the body's last conv adds shortcut(x) in its epilogue
+        (one launch instead of conv + add); any other shape of the tree - e.g. an adapter
+        spliced after the last conv - takes the generic Sum path."""
+        if len(inputs) == 1 and isinstance(inputs[0], Tensor) and inputs[0].is_cuda and B.fusion_enabled() and len(self) == 2:
+            body, shortcut = self[0], self[1]
+            if type(body) is fl.Chain and body._steps()[-1][0] == "call":
+                last = fusion.tail_conv(body)
+                if last is not None:
+                    skip = shortcut(*inputs)
+                    h = body._run_children(inputs, skip_last=True)
+                    if isinstance(h, Tensor) and isinstance(skip, Tensor):
+                        name = next(reversed(body._modules))
+                        out = body._call_fused(name, lambda t: B.conv2d_module(t, last, residual=skip), h)
+                        body._reset_context()
+                        return out
+                    raise RuntimeError("ResidualBlock: unexpected non-tensor intermediate")
+        return fl.Sum.forward(self, *inputs)
 
 
 class ResidualAccumulator(fl.Passthrough):
