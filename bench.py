@@ -38,6 +38,13 @@ METRIC = "SDXL 1024^2 bf16 denoising steps/s (latent batch 8, CFG, Euler)"
 UNIT = "steps/s"
 
 
+T0 = time.time()
+
+
+def log(msg: str) -> None:
+    print(f"[bench {time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def measured_peaks() -> tuple[dict, str]:
     path = ROOT / "MEASURED_PEAKS.json"
     if path.exists():
@@ -204,6 +211,7 @@ def run_gpu_arm(args) -> None:
     B.load_library()
     dtype = torch.bfloat16
     manual_seed(0)
+    log('building SDXLUNet (random init on device)')
     unet = SDXLUNet(in_channels=4, device=device, dtype=dtype)
     if world > 1:  # identical replicas: weights come from rank 0 over NCCL/NVLink, once
         for prm in unet.parameters():
@@ -212,6 +220,7 @@ def run_gpu_arm(args) -> None:
     if not args.no_graph and not args.profile_step:
         sdxl.enable_cuda_graph()
 
+    log('model ready')
     g = torch.Generator().manual_seed(1000 + rank)
     lb = args.latent_batch
     host = {
@@ -262,6 +271,7 @@ def run_gpu_arm(args) -> None:
         x = dev["x"]
         for s in range(max(args.warmup, 3)):  # includes the capture
             step_resident(x, s)
+        log('warm-up / capture done')
         launches0 = B.launch_count()
         runner = sdxl._graphed_unet[0] if sdxl._graphed_unet else None
         replays0 = runner.replays if runner else 0
@@ -279,6 +289,7 @@ def run_gpu_arm(args) -> None:
         graph_launches = (runner.replays - replays0) * runner.launches_per_replay if runner else 0
         gpu_launches = eager_launches + graph_launches
 
+        log(f'resident loop done: {ms_total / args.steps:.2f} ms/step')
         # end to end: host buffers in, host result out, every step
         for s in range(3):
             step_e2e(s)
@@ -302,8 +313,10 @@ def run_gpu_arm(args) -> None:
             dist.destroy_process_group()
         return
 
+    log(f'e2e loop done: {ms_e2e / args.steps:.2f} ms/step')
     peaks, peaks_kind = measured_peaks()
     roofline = dominant_kernel_roofline(device, peaks, peaks_kind)
+    log('kernel roofline done')
     step_tflops = SDXL_TFLOP_PER_SAMPLE * 2 * lb / (ms_per_step * 1e-3)
     roofline_step = {
         "bound": "tensor", "achieved": step_tflops, "peak": float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])),
@@ -314,7 +327,9 @@ def run_gpu_arm(args) -> None:
     cpu = None
     if not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
+        log(f'cpu baseline on {threads} threads')
         dt_row, sample = cpu_reference_step_seconds(1, 1, threads)
+        log('cpu baseline done')
         cpu = {"value": 1.0 / (dt_row * CFG_ROWS), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                "seconds_per_sample": dt_row}
     line = {

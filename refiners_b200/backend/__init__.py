@@ -157,27 +157,50 @@ def _same(x: Tensor, *others: Tensor | None) -> None:
 
 # ------------------------------------------------------------------------------------ caches
 class _PackCache:
-    """Derived tensors keyed on the identity of their sources (storage pointer, version, shape)."""
+    """Derived tensors (packed weights) cached per SOURCE TENSOR OBJECT.
 
-    def __init__(self, limit: int = 8192) -> None:
-        self._items: dict[tuple[Any, ...], Tensor | tuple[Tensor, ...]] = {}
-        self._limit = limit
+    Keyed on ``id()`` of the source tensors and validated with weak references plus
+    (data_ptr, _version): a storage address alone is not an identity - the caching allocator
+    hands a freed weight's address to the next model's weight of the same shape - and the
+    reference swaps ``.weight`` objects (lora.py:168-178, image_prompt.py:344-347), moves them
+    with ``.to()`` and edits them in place.  Entries die with their source tensor."""
+
+    def __init__(self) -> None:
+        self._items: dict[tuple[Any, ...], tuple[tuple[Any, ...], Any]] = {}
 
     @staticmethod
     def key(*tensors: Tensor | None) -> tuple[Any, ...]:
+        return tuple(None if t is None else id(t) for t in tensors)
+
+    @staticmethod
+    def _stamp(tensors: Sequence[Tensor | None]) -> tuple[Any, ...]:
         return tuple(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in tensors)
 
-    def get(self, key: tuple[Any, ...]) -> Any:
-        return self._items.get(key)
+    def get(self, key: tuple[Any, ...], tensors: Sequence[Tensor | None]) -> Any:
+        hit = self._items.get(key)
+        if hit is None:
+            return None
+        refs, stamp, value = hit
+        if stamp != self._stamp(tensors) or any((r is None) != (t is None) or (r is not None and r() is not t) for r, t in zip(refs, tensors)):
+            del self._items[key]
+            return None
+        return value
 
-    def put(self, key: tuple[Any, ...], value: Any) -> Any:
-        if len(self._items) >= self._limit:
-            self._items.clear()
-        self._items[key] = value
+    def put(self, key: tuple[Any, ...], tensors: Sequence[Tensor | None], value: Any) -> Any:
+        import weakref
+
+        def drop(_ref: Any, key: tuple[Any, ...] = key, items: dict = self._items) -> None:
+            items.pop(key, None)
+
+        refs = tuple(None if t is None else weakref.ref(t, drop) for t in tensors)
+        self._items[key] = (refs, self._stamp(tensors), value)
         return value
 
     def clear(self) -> None:
         self._items.clear()
+
+    def __len__(self) -> int:
+        return len(self._items)
 
 
 _conv_cache = _PackCache()
@@ -513,8 +536,9 @@ _ops = torch.ops.refiners_b200
 # ----------------------------------------------------------------------------- public helpers
 def pack_loras(x: Tensor, w: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> tuple[Tensor, Tensor, Tensor]:
     """(down_cat[r_pad, K], up_cat[N, r_pad], colscale[r_pad]) for rb200_linear, cached."""
-    key = _PackCache.key(*[t for d, u, _ in loras for t in (d, u)]) + tuple(s for _, _, s in loras)
-    hit = _lora_cache.get(key)
+    sources = [t for d, u, _ in loras for t in (d, u)]
+    key = _PackCache.key(*sources) + tuple(float(s) for _, _, s in loras)
+    hit = _lora_cache.get(key, sources)
     if hit is not None:
         return hit
     lib = load_library()
@@ -539,7 +563,7 @@ def pack_loras(x: Tensor, w: Tensor, loras: Sequence[tuple[Tensor, Tensor, float
             colscale.data_ptr(), r_pad,
         )
     )
-    return _lora_cache.put(key, (down_cat, up_cat, colscale))
+    return _lora_cache.put(key, sources, (down_cat, up_cat, colscale))
 
 
 def lora_fusable(x: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> bool:
@@ -566,7 +590,7 @@ def linear_geglu(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
     """``GLU(GeLU)(Linear(x))`` in one launch; the value/gate interleave of W is cached."""
     _inference_only(x, weight, bias)
     key = _PackCache.key(weight, bias)
-    packed = _geglu_cache.get(key)
+    packed = _geglu_cache.get(key, (weight, bias))
     if packed is None:
         lib = load_library()
         w = weight.contiguous()
@@ -577,7 +601,7 @@ def linear_geglu(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
                 _stream(), _dtype_code(w), w.data_ptr(), _ptr(bias), wp.data_ptr(), _ptr(bp), w.shape[0] // 2, w.shape[1]
             )
         )
-        packed = _geglu_cache.put(key, (wp, bp))
+        packed = _geglu_cache.put(key, (weight, bias), (wp, bp))
     wp, bp = packed
     return _ops.linear(x, wp, bp, None, None, None, None, EPI_GEGLU)
 
@@ -588,14 +612,14 @@ def geglu_fusable(weight: Tensor) -> bool:
 
 def packed_conv_weight(weight: Tensor) -> Tensor:
     key = _PackCache.key(weight)
-    packed = _conv_cache.get(key)
+    packed = _conv_cache.get(key, (weight,))
     if packed is None:
         lib = load_library()
         w = weight.contiguous()
         Cout, Cin, R, S = w.shape
         packed = torch.empty((R * S, Cout, Cin), device=w.device, dtype=w.dtype)
         _check(lib.rb200_conv2d_pack_weight(_stream(), _dtype_code(w), w.data_ptr(), packed.data_ptr(), Cout, Cin, R, S))
-        _conv_cache.put(key, packed)
+        _conv_cache.put(key, (weight,), packed)
     return packed
 
 

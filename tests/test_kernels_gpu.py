@@ -373,3 +373,21 @@ def test_cuda_graph_capture(cuda_device):
         graph.replay()
         torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_packed_weight_cache_is_not_fooled_by_address_reuse(cuda_device):
+    """The allocator hands a freed weight's address to the next tensor of the same shape; the
+    packed-weight cache must key on tensor identity, not on the address."""
+    from refiners_b200 import backend as B
+
+    x = torch.randn(1, 64, 8, 8, device=cuda_device, dtype=torch.bfloat16)
+    outs, refs, ptrs = [], [], []
+    for seed in (1, 2, 3):
+        w = (_gen((64, 64, 3, 3), seed) * 0.05).to(cuda_device, torch.bfloat16)
+        ptrs.append(w.data_ptr())
+        with torch.no_grad():
+            outs.append(B.conv2d(x, w, None, 1, 1).float().cpu())
+        refs.append(F.conv2d(x.float().cpu(), w.float().cpu(), None, padding=1))
+        del w
+    for o, r in zip(outs, refs):
+        assert_close(o, r, torch.bfloat16, what="conv after weight replacement")
