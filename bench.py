@@ -111,8 +111,11 @@ def cpu_reference_step_seconds(warmup: int, steps: int, threads: int) -> tuple[f
     """Time the oracle port of the reference's SDXL UNet on the host cores (fp32).
     Bounded sample: ONE UNet-batch row (1/16 of a batch-8 CFG step) at the full 1024^2
     resolution per timed iteration."""
+    from oracle import ops as oops
     from oracle import unet as ounet
     from oracle.weights import keyed_state_dict
+
+    oops.FAST = True  # call the same fused ATen CPU kernels the reference calls (see oracle/ops.py)
     from refiners_b200.foundationals.latent_diffusion import SDXLUNet
 
     torch.set_num_threads(threads)
@@ -130,7 +133,7 @@ def cpu_reference_step_seconds(warmup: int, steps: int, threads: int) -> tuple[f
         for _ in range(steps):
             ounet.sdxl_unet(sd, x, ts, ctx, pooled, ids)
         dt = (time.perf_counter() - t0) / steps
-    return dt, "1 UNet-batch row (1/16 of a latent-batch-8 CFG step) at 128x128 latents, fp32, oracle port"
+    return dt, "1 UNet-batch row (1/16 of a latent-batch-8 CFG step) at 128x128 latents, fp32, oracle port calling the reference's ATen CPU ops"
 
 
 def run_reference_arm(args) -> None:
@@ -214,8 +217,9 @@ def run_gpu_arm(args) -> None:
     log('building SDXLUNet (random init on device)')
     unet = SDXLUNet(in_channels=4, device=device, dtype=dtype)
     if world > 1:  # identical replicas: weights come from rank 0 over NCCL/NVLink, once
-        for prm in unet.parameters():
-            dist.broadcast(prm.data, src=0)
+        from refiners_b200.engine.sharding import broadcast_parameters
+
+        broadcast_parameters(unet, src=0)
     sdxl = StableDiffusion_XL(unet=unet, solver=Euler(num_inference_steps=30), device=device, dtype=dtype)
     if not args.no_graph and not args.profile_step:
         sdxl.enable_cuda_graph()

@@ -12,9 +12,19 @@ import math
 import torch
 from torch import Tensor
 
+# The timed CPU baseline (bench.py `cpu_baseline` / `--impl reference`) must cost what the
+# REFERENCE costs on the host, and the reference calls ATen's fused CPU kernels:
+#   F.conv2d (conv.py:6), F.scaled_dot_product_attention (attentions.py:29-34),
+#   F.group_norm / F.layer_norm (norm.py:14,52), F.linear (linear.py:9).
+# With FAST = True the functions below make exactly those calls; the default (False) keeps the
+# independent elementary-op restatement that the parity tests check the kernels against.
+FAST = False
+
 
 def linear(x: Tensor, weight: Tensor, bias: Tensor | None = None) -> Tensor:
     """y = x W^T + b.  Reference: fluxion/layers/linear.py:9-58 (torch.nn.Linear.forward)."""
+    if FAST:
+        return torch.nn.functional.linear(x, weight, bias)
     y = x @ weight.transpose(-1, -2)
     return y if bias is None else y + bias
 
@@ -22,6 +32,8 @@ def linear(x: Tensor, weight: Tensor, bias: Tensor | None = None) -> Tensor:
 def conv2d(x: Tensor, weight: Tensor, bias: Tensor | None, stride: int = 1, padding: int = 0) -> Tensor:
     """Zero-padded cross-correlation, NCHW.  Reference: fluxion/layers/conv.py:6-61.
     Restated as unfold (im2col) + matmul."""
+    if FAST:
+        return torch.nn.functional.conv2d(x, weight, bias, stride=stride, padding=padding)
     B, C, H, W = x.shape
     Co, Ci, R, S = weight.shape
     assert Ci == C
@@ -37,6 +49,8 @@ def conv2d(x: Tensor, weight: Tensor, bias: Tensor | None, stride: int = 1, padd
 def group_norm(x: Tensor, num_groups: int, weight: Tensor, bias: Tensor, eps: float) -> Tensor:
     """Per (sample, group) standardisation with biased variance, then per-channel affine.
     Reference: fluxion/layers/norm.py:52-92 (torch.nn.GroupNorm)."""
+    if FAST:
+        return torch.nn.functional.group_norm(x, num_groups, weight, bias, eps)
     B, C = x.shape[:2]
     g = x.reshape(B, num_groups, -1)
     mean = g.mean(dim=-1, keepdim=True)
@@ -48,6 +62,8 @@ def group_norm(x: Tensor, num_groups: int, weight: Tensor, bias: Tensor, eps: fl
 
 def layer_norm(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tensor:
     """Row standardisation over the last dim.  Reference: fluxion/layers/norm.py:14-49."""
+    if FAST:
+        return torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
     mean = x.mean(dim=-1, keepdim=True)
     var = ((x - mean) ** 2).mean(dim=-1, keepdim=True)
     return (x - mean) / torch.sqrt(var + eps) * weight + bias
@@ -62,11 +78,15 @@ def layer_norm_2d(x: Tensor, weight: Tensor, bias: Tensor, eps: float) -> Tensor
 
 def silu(x: Tensor) -> Tensor:
     """x * sigmoid(x).  Reference: fluxion/layers/activations.py:31-41."""
+    if FAST:
+        return torch.nn.functional.silu(x)
     return x / (1.0 + torch.exp(-x))
 
 
 def gelu(x: Tensor) -> Tensor:
     """Exact (erf) GeLU.  Reference: fluxion/layers/activations.py:83-114 (approximation NONE)."""
+    if FAST:
+        return torch.nn.functional.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
@@ -86,6 +106,9 @@ def sdpa(q: Tensor, k: Tensor, v: Tensor, num_heads: int, is_causal: bool = Fals
     qh = q.reshape(B, Sq, num_heads, d).transpose(1, 2)
     kh = k.reshape(B, Sk, num_heads, d).transpose(1, 2)
     vh = v.reshape(B, Sk, num_heads, d).transpose(1, 2)
+    if FAST:
+        o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh, is_causal=is_causal)
+        return o.transpose(1, 2).reshape(B, Sq, C)
     logits = (qh @ kh.transpose(-1, -2)) / math.sqrt(d)
     if is_causal:
         mask = torch.ones(Sq, Sk, dtype=torch.bool).tril()

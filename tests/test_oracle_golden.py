@@ -87,3 +87,18 @@ def test_sd1_unet_full():
     shapes = {k: tuple(v.shape) for k, v in SD1UNet(4, device="meta").state_dict().items()}
     sd = keyed_state_dict(shapes, seed=1)
     close(ounet.sd1_unet(sd, f["sd1.x"], f["sd1.timestep"], f["sd1.ctx"]), f["sd1.y"], rel=2e-5)
+
+
+def test_fast_mode_matches_golden():
+    """oracle.ops.FAST (the fused ATen CPU calls the reference itself makes; used only for the timed
+    CPU baseline) is pinned to the same golden vectors."""
+    f = load_file(str(GOLDEN / "blocks.safetensors"))
+    ops.FAST = True
+    try:
+        for tag in ("res_same", "res_proj"):
+            close(ounet.residual_block(sub(f, f"{tag}.sd."), "ResidualBlock", f[f"{tag}.x"], f[f"{tag}.temb"]), f[f"{tag}.y"])
+        for tag, lin in (("xattn_linear", True), ("xattn_conv", False)):
+            sd = {"X." + k: v for k, v in sub(f, f"{tag}.sd.").items()}
+            close(ounet.cross_attention_2d(sd, "X", f[f"{tag}.x"], f[f"{tag}.ctx"], 2, 2, lin), f[f"{tag}.y"])
+    finally:
+        ops.FAST = False

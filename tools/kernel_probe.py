@@ -1,0 +1,61 @@
+"""Launch one hot kernel a few times in isolation (for `ncu --set full -k regex:<name>`).
+
+    python tools/kernel_probe.py gemm        # [16384,1280] x [1280,1280]^T  (dominant SDXL Linear)
+    python tools/kernel_probe.py conv        # 3x3 1280->1280 @ 32x32, batch 16
+    python tools/kernel_probe.py attn        # self-attention B=16 H=20 S=1024 d=64
+    python tools/kernel_probe.py attn4096    # self-attention B=16 H=10 S=4096 d=64
+Also prints CUDA-event timings (L2 flushed between launches)."""
+
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from refiners_b200 import backend as B  # noqa: E402
+
+dev = torch.device("cuda")
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+bf = torch.bfloat16
+flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+if which == "gemm":
+    M, K, N = 16384, 1280, 1280
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
+elif which == "gemm_ff":
+    M, K, N = 16384, 1280, 10240
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
+elif which == "conv":
+    x = torch.randn(16, 1280, 32, 32, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(1280, 1280, 3, 3, device=dev, dtype=bf) * 0.01
+    fn, flops = (lambda: B.conv2d(x, w, None, 1, 1)), 2.0 * 16 * 1024 * 1280 * 1280 * 9
+elif which == "conv320":
+    x = torch.randn(16, 320, 128, 128, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(320, 320, 3, 3, device=dev, dtype=bf) * 0.02
+    fn, flops = (lambda: B.conv2d(x, w, None, 1, 1)), 2.0 * 16 * 16384 * 320 * 320 * 9
+elif which in ("attn", "attn4096"):
+    Bn, H, S = (16, 20, 1024) if which == "attn" else (16, 10, 4096)
+    q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
+    k, v = torch.randn_like(q), torch.randn_like(q)
+    fn, flops = (lambda: B.sdpa(q, k, v, H)), 4.0 * Bn * H * S * S * 64
+else:
+    raise SystemExit(f"unknown probe {which}")
+
+with torch.no_grad():
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+ms = sorted(times)[len(times) // 2]
+print(f"{which}: median {ms * 1e3:.1f} us, {flops / ms / 1e9:.1f} TFLOP/s ({flops / 1e9:.1f} GFLOP per launch)")
