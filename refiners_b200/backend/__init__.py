@@ -206,12 +206,14 @@ class _PackCache:
 _conv_cache = _PackCache()
 _geglu_cache = _PackCache()
 _lora_cache = _PackCache()
+_concat_cache = _PackCache()
 
 
 def clear_caches() -> None:
     _conv_cache.clear()
     _geglu_cache.clear()
     _lora_cache.clear()
+    _concat_cache.clear()
 
 
 # ------------------------------------------------------------------------- raw op kernels
@@ -604,6 +606,18 @@ def linear_geglu(x: Tensor, weight: Tensor, bias: Tensor | None) -> Tensor:
         packed = _geglu_cache.put(key, (weight, bias), (wp, bp))
     wp, bp = packed
     return _ops.linear(x, wp, bp, None, None, None, None, EPI_GEGLU)
+
+
+def concat_linear_weights(weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> tuple[Tensor, Tensor | None]:
+    """Row-concatenation of sibling Linear weights (fused q/k/v projection), cached per source tensors."""
+    sources = list(weights) + list(biases)
+    key = _PackCache.key(*sources)
+    hit = _concat_cache.get(key, sources)
+    if hit is not None:
+        return hit
+    w = torch.cat([t.detach() for t in weights], dim=0).contiguous()
+    b = None if biases[0] is None else torch.cat([t.detach() for t in biases if t is not None], dim=0).contiguous()
+    return _concat_cache.put(key, sources, (w, b))
 
 
 def geglu_fusable(weight: Tensor) -> bool:

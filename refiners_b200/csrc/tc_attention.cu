@@ -10,6 +10,8 @@
 //   warps 2..5  softmax: thread = query row (TMEM lane): tcgen05.ld S, online max / exp2 / sum in
 //               fp32, P -> bf16 -> swizzled smem (the A operand of the second MMA), and the running
 //               output is kept in registers: O = O * alpha + O_j (tcgen05.ld of the 64-col O_j).
+// S, P and O_j are double buffered so that the tensor core computes S_{j+1} and O_j while the
+// softmax warps work on tile j: the softmax warps never wait for an MMA in steady state.
 // The [B, S, H*D] operands are addressed in place through 4D tensor maps (D, H, S, B): the head
 // split/merge of the reference (fluxion/layers/attentions.py:177-202) costs no copies.
 // The Sq x Sk score matrix never exists in memory.
@@ -26,8 +28,8 @@ constexpr int HD = 64;    // head dim
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 192;
 constexpr int Q_BYTES = QT * HD * 2, K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2, P_BYTES = QT * KT * 2;
-constexpr int TMEM_COLS = 128;  // S: cols [0, 64), O: cols [64, 128)
-constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + P_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 256;  // S[2]: cols [0, 128), O[2]: cols [128, 256) - double buffered
+constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
 
 struct AttnParams {
   void* o;
@@ -149,10 +151,11 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* kv_empty = bars + STAGES;    // [STAGES]
   uint64_t* q_full = bars + 2 * STAGES;
   uint64_t* q_empty = q_full + 1;
-  uint64_t* bar_s = q_full + 2;          // S tile ready in TMEM
-  uint64_t* bar_p = q_full + 3;          // P tile written to smem (S and previous O consumed)
-  uint64_t* bar_o = q_full + 4;          // O_j ready in TMEM (P and V slot consumed)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 5);
+  uint64_t* bar_s = q_full + 2;          // [2] S tile ready in TMEM buffer b
+  uint64_t* bar_sfree = q_full + 4;      // [2] S buffer b has been read by the softmax warps
+  uint64_t* bar_p = q_full + 6;          // [2] P tile written to smem buffer b (previous O consumed)
+  uint64_t* bar_o = q_full + 8;          // [2] O_j ready in TMEM buffer b (P buffer and V slot consumed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsets = DUAL ? 2 : 1;
@@ -167,9 +170,12 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_p, 4);
-    mbar_init(bar_o, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_s[b], 1);
+      mbar_init(&bar_sfree[b], 4);
+      mbar_init(&bar_p[b], 4);
+      mbar_init(&bar_o[b], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -180,7 +186,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;  // buffer b at + 64 * b
 
   if (warp == 0) {
     // ================================================================================ TMA
@@ -214,10 +220,24 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   } else if (warp == 1) {
     // ================================================================================ MMA
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0, qphase = 0, pphase = 0;
+      int st_s = 0, st_pv = 0;      // ring cursors: stage whose K feeds the next S / whose V feeds the next PV
+      uint32_t ph_s = 0, qphase = 0;
+      uint32_t g = 0;               // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
       const uint64_t dq = desc_kmajor(smem_u32(sQ));
-      const uint64_t dp = desc_kmajor(smem_u32(sP));
+      auto issue_s = [&](uint32_t gt) {
+        const uint32_t b = gt & 1, k_use = gt >> 1;
+        mbar_wait(&kv_full[st_s], ph_s);
+        mbar_wait(&bar_sfree[b], (k_use & 1) ^ 1);  // previous S in this buffer has been read
+        tcgen05_fence_after();
+        const uint64_t dk = desc_kmajor(smem_u32(sK + st_s * K_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s + b * 64, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+        umma_commit(&bar_s[b]);
+        if (++st_s == STAGES) {
+          st_s = 0;
+          ph_s ^= 1;
+        }
+      };
       for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
         mbar_wait(q_full, qphase);
         qphase ^= 1;
@@ -225,40 +245,22 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int set = 0; set < nsets; ++set) {
           const int64_t Sk = set ? p.Sk2 : p.Sk;
           const int ntiles = int((Sk + KT - 1) / KT);
-          // S_0 = Q K_0^T
-          mbar_wait(&kv_full[stage], phase);
-          tcgen05_fence_after();
-          {
-            const uint64_t dk = desc_kmajor(smem_u32(sK + stage * K_BYTES));
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
-          }
-          umma_commit(bar_s);
-          for (int j = 0; j < ntiles; ++j) {
-            // P_j is in smem, S_j and O_{j-1} have been read by the softmax warps
-            mbar_wait(bar_p, pphase);
-            pphase ^= 1;
+          issue_s(g);
+          for (int j = 0; j < ntiles; ++j, ++g) {
+            if (j + 1 < ntiles) issue_s(g + 1);  // S_{j+1} runs while the softmax warps work on S_j
+            const uint32_t b = g & 1;
+            mbar_wait(&bar_p[b], (g >> 1) & 1);  // P_j in smem buffer b; O buffer b has been drained
             tcgen05_fence_after();
-            const uint64_t dv = desc_mnmajor(smem_u32(sV + stage * V_BYTES), V_BYTES);
+            const uint64_t dp = desc_kmajor(smem_u32(sP + b * P_BYTES));
+            const uint64_t dv = desc_mnmajor(smem_u32(sV + st_pv * V_BYTES), V_BYTES);
 #pragma unroll
             for (int k = 0; k < KT / 16; ++k) {
               // A: +32 B per 16 keys inside the swizzle atom; B (MN-major): +16 rows * 128 B
-              umma_f16(tmem_o, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
+              umma_f16(tmem_o + b * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
             }
-            umma_commit(&kv_empty[stage]);  // K_j / V_j slot free once these MMAs retire
-            umma_commit(bar_o);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-            if (j + 1 < ntiles) {
-              mbar_wait(&kv_full[stage], phase);
-              tcgen05_fence_after();
-              const uint64_t dk = desc_kmajor(smem_u32(sK + stage * K_BYTES));
-#pragma unroll
-              for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
-              umma_commit(bar_s);
-            }
+            umma_commit(&kv_empty[st_pv]);  // K_j / V_j slot free once these MMAs retire
+            umma_commit(&bar_o[b]);
+            if (++st_pv == STAGES) st_pv = 0;
           }
         }
         umma_commit(q_empty);  // every MMA reading Q has been issued; the slot frees when they retire
@@ -269,7 +271,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const uint32_t lane_off = uint32_t(lg * 32) << 16;
-    uint32_t sphase = 0, ophase = 0;
+    uint32_t g = 0;  // global tile counter, in step with the MMA warp
     uint8_t* prow = sP + row * 128;
     const int sw = row & 7;
     T* obase = static_cast<T*>(p.o);
@@ -289,15 +291,15 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < HD; ++i) acc[i] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < ntiles; ++j) {
-          mbar_wait(bar_s, sphase);
-          sphase ^= 1;
+        for (int j = 0; j < ntiles; ++j, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(&bar_s[buf], (g >> 1) & 1);
           tcgen05_fence_after();
           float s[KT];
           {
             uint32_t raw0[32], raw1[32];
-            tmem_ld_32x32(tmem_s + lane_off, raw0);
-            tmem_ld_32x32(tmem_s + lane_off + 32, raw1);
+            tmem_ld_32x32(tmem_s + buf * 64 + lane_off, raw0);
+            tmem_ld_32x32(tmem_s + buf * 64 + lane_off + 32, raw1);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -305,6 +307,9 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
               s[32 + i] = __uint_as_float(raw1[i]);
             }
           }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_sfree[buf]);  // the tensor core may overwrite this S buffer
           const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT);
           if (valid < KT) {
 #pragma unroll
@@ -329,40 +334,41 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           l_run = l_run * alpha + psum;
           m_run = m_new;
           if (j > 0) {
-            // O_{j-1} = P_{j-1} V_{j-1} has landed: fold it in, then rescale to the new maximum
-            mbar_wait(bar_o, ophase);
-            ophase ^= 1;
+            // O_{j-1} = P_{j-1} V_{j-1} landed long ago: fold it in, then rescale to the new maximum
+            const uint32_t gp = g - 1, bp = gp & 1;
+            mbar_wait(&bar_o[bp], (gp >> 1) & 1);
             tcgen05_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               uint32_t raw[32];
-              tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
+              tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) acc[half * 32 + i] = (acc[half * 32 + i] + __uint_as_float(raw[i])) * alpha;
             }
           }
-          // P_j -> smem, K-major with the 128B swizzle the MMA descriptor expects
+          // P_j -> smem buffer, K-major with the 128B swizzle the MMA descriptor expects.  The buffer
+          // was last read by PV_{j-2}, whose completion (bar_o) this thread has already observed.
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 v = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-            *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = v;
+            *reinterpret_cast<uint4*>(prow + buf * P_BYTES + ((c ^ sw) << 4)) = v;
           }
           fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_p);
+          if (lane == 0) mbar_arrive(&bar_p[buf]);
         }
         // last tile of the set
-        mbar_wait(bar_o, ophase);
-        ophase ^= 1;
-        tcgen05_fence_after();
         {
+          const uint32_t gp = g - 1, bp = gp & 1;
+          mbar_wait(&bar_o[bp], (gp >> 1) & 1);
+          tcgen05_fence_after();
           const float wgt = (set ? p.scale2 : 1.f) * (l_run > 0.f ? 1.f / l_run : 0.f);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t raw[32];
-            tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
+            tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -372,8 +378,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
           }
         }
-        // the next set (or work item) reuses the O accumulator in TMEM only after a new P tile is
-        // published, which happens after these loads - no extra fence needed here
       }
       float* fin = DUAL ? out : acc;
       const int64_t qi = int64_t(qt) * QT + row;

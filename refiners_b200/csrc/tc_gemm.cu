@@ -17,6 +17,8 @@
 // An optional second K segment (A2, B2) appends extra K blocks; LoRA up-projections use it.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rb200 {
@@ -96,6 +98,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// B-tile half loaded once from L2 and written into the same smem offset of every CTA in `mask`;
+// each destination CTA's mbarrier (same offset) receives the complete_tx for these bytes
+__device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -125,6 +144,11 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -191,7 +215,11 @@ constexpr size_t smem_bytes() {
 }
 
 // --------------------------------------------------------------------------------- the kernel
-template <typename T, int BN>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs own vertically adjacent output tiles
+// (same N range): each loads its own A tile and HALF of the shared B tile, multicast into both
+// CTAs' smem - L2->SM traffic per CTA-iteration drops from A+B to A+B/2 (48 KB -> 32 KB at
+// BN = 256), which matters because the kernel is L2-bandwidth- rather than MMA-bound.
+template <typename T, int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
@@ -212,7 +240,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int cta_rank = CL > 1 ? int(cluster_ctarank()) : 0;
+  const int cluster_id = int(blockIdx.x) / CL, num_clusters = int(gridDim.x) / CL;
+  // work items are groups of CL vertically adjacent tiles; an odd tail gets a phantom tile whose
+  // loads are out-of-bounds zeros and whose stores are masked
+  const int num_groups = ((p.tiles_m + CL - 1) / CL) * p.tiles_n;
   const int k_iters = p.k_iters1 + p.k_iters2;
 
   if (warp == 0 && lane == 0) {
@@ -224,7 +256,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);  // every CTA that reads this slot (it is written by all of them)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -235,6 +267,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers exist before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -243,8 +276,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+        const int mg = grp / p.tiles_n, nt = grp - mg * p.tiles_n;
+        const int mt = mg * CL + cta_rank;
         int a1, a2, a3;  // A coordinates of dims 1..3 at tap (0, 0)
         if (p.conv) {
           const int per_img = p.tiles_h * p.tiles_w;
@@ -268,7 +302,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (it < p.k_iters1) {
             const int r = tap / p.kw, s = tap - r * p.kw;
             tma_load_4d(da, &map_a, &full_bar[stage], kb * BK, a1 + s, a2 + r, a3);
-            tma_load_3d(db, &map_b, &full_bar[stage], kb * BK, n0, tap);
+            if constexpr (CL > 1) {
+              // my half of the shared B tile, delivered to both CTAs
+              tma_load_3d_mcast(static_cast<uint8_t*>(db) + cta_rank * (B_BYTES / CL), &map_b, &full_bar[stage], kb * BK,
+                                n0 + cta_rank * (BN / CL), tap, uint16_t((1u << CL) - 1));
+            } else {
+              tma_load_3d(db, &map_b, &full_bar[stage], kb * BK, n0, tap);
+            }
             if (++kb == p.kblocks) {
               kb = 0;
               ++tap;
@@ -276,7 +316,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             const int kb2 = it - p.k_iters1;
             tma_load_4d(da, &map_a2, &full_bar[stage], kb2 * BK, mt * BM, 0, 0);
-            tma_load_3d(db, &map_b2, &full_bar[stage], kb2 * BK, n0, 0);
+            if constexpr (CL > 1) {
+              tma_load_3d_mcast(static_cast<uint8_t*>(db) + cta_rank * (B_BYTES / CL), &map_b2, &full_bar[stage], kb2 * BK,
+                                n0 + cta_rank * (BN / CL), 0, uint16_t((1u << CL) - 1));
+            } else {
+              tma_load_3d(db, &map_b2, &full_bar[stage], kb2 * BK, n0, 0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -292,7 +337,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
@@ -307,7 +352,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // 16-byte-granular start-address field
             umma_f16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in every CTA that writes into it) when these MMAs retire
+          if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], uint16_t((1u << CL) - 1));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -331,8 +378,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool geglu = p.epilogue == RB200_EPI_GEGLU;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+    for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
+      const int mg = grp / p.tiles_n, nt = grp - mg * p.tiles_n;
+      const int mt = mg * CL + cta_rank;
       int64_t m_lin, b_idx = 0;
       bool valid;
       if (p.conv) {
@@ -343,7 +391,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ih = irem / p.TW, iw = irem - ih * p.TW;
         b_idx = int64_t(tb) * p.TB + ib;
         m_lin = (b_idx * p.Ho + (int64_t(th) * p.TH + ih)) * p.Wo + (int64_t(tw) * p.TW + iw);
-        valid = m_lin < p.M;
+        valid = mt < p.tiles_m && m_lin < p.M;
       } else {
         m_lin = int64_t(mt) * BM + row;
         valid = m_lin < p.M;
@@ -463,6 +511,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still write/signal here
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -520,23 +569,52 @@ bool pick_conv_tile(int64_t B, int64_t Ho, int64_t Wo, int* TW, int* TH, int* TB
   return false;
 }
 
-template <typename T, int BN>
-int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mb2,
-              TcParams& prm) {
+template <typename T, int BN, int CL>
+int launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mb2,
+                 TcParams& prm) {
   static bool configured = false;
   constexpr size_t SMEM = smem_bytes<BN>();
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<T, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<T, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
       RB200_FAIL(-2, "tc_gemm: cannot reserve %zu bytes of shared memory", SMEM);
     configured = true;
   }
-  prm.tiles_n = int(ceil_div(prm.N, BN));
-  const int64_t tiles = int64_t(prm.tiles_m) * prm.tiles_n;
-  if (tiles > (int64_t(1) << 30)) RB200_FAIL(-1, "tc_gemm: too many tiles");
-  const int grid = int(tiles < sm_count() ? tiles : sm_count());
-  tc_gemm_kernel<T, BN><<<grid, NUM_THREADS, SMEM, st>>>(ma, mb, ma2, mb2, prm);
+  const int64_t groups = int64_t((prm.tiles_m + CL - 1) / CL) * prm.tiles_n;
+  if (groups > (int64_t(1) << 30)) RB200_FAIL(-1, "tc_gemm: too many tiles");
+  const int64_t max_clusters = sm_count() / CL;
+  const int clusters = int(groups < max_clusters ? groups : max_clusters);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(clusters * CL));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<T, BN, CL>, ma, mb, ma2, mb2, prm);
+  if (e != cudaSuccess) RB200_FAIL(-2, "tc_gemm launch: %s", cudaGetErrorString(e));
   RB200_CHECK_LAUNCH("tc_gemm");
   return 0;
+}
+
+int cluster_mode() {
+  static const int mode = [] {
+    const char* e = getenv("RB200_GEMM_CLUSTER");  // 1 disables the multicast pairing (A/B runs)
+    return e ? atoi(e) : 2;
+  }();
+  return mode;
+}
+
+template <typename T, int BN>
+int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mb2,
+              TcParams& prm, int cl) {
+  prm.tiles_n = int(ceil_div(prm.N, BN));
+  if (cl == 2) return launch_tc_cl<T, BN, 2>(st, ma, mb, ma2, mb2, prm);
+  return launch_tc_cl<T, BN, 1>(st, ma, mb, ma2, mb2, prm);
 }
 
 int pick_bn(int64_t M_tiles, int64_t N) {
@@ -623,14 +701,15 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
     const uint64_t bdims[3] = {uint64_t(p.Cin), uint64_t(p.N), uint64_t(p.R * p.S)};
     const uint64_t bstr[2] = {uint64_t(p.Cin) * 2, uint64_t(p.N) * p.Cin * 2};
     const int bn = pick_bn(prm.tiles_m, p.N);
-    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn), 1};
+    const int cl = (cluster_mode() >= 2 && prm.tiles_m >= 2) ? 2 : 1;
+    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn / cl), 1};  // each CTA of a pair loads half of the B tile
     if (int rc = make_map(&mb, p.dtype, p.b, 3, bdims, bstr, bbox, ones)) return rc;
     ma2 = ma; mb2 = mb;
     prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
     const bool bf = p.dtype == RB200_BF16;
-    if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm);
-    if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm);
-    return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm);
+    if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm, cl);
+    if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm, cl);
+    return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm, cl);
   }
 
   prm.tiles_m = int(ceil_div(p.M, BM));
@@ -640,6 +719,7 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
   prm.k_iters2 = p.K2 ? int(p.K2 / BK) : 0;
   prm.TW = BM; prm.TH = 1; prm.TB = 1; prm.tiles_w = 1; prm.tiles_h = 1;
   const int bn = pick_bn(prm.tiles_m, p.N);
+  const int cl = (cluster_mode() >= 2 && prm.tiles_m >= 2) ? 2 : 1;
   {
     const uint64_t dims[4] = {uint64_t(p.K), uint64_t(p.M), 1, 1};
     const uint64_t strides[3] = {uint64_t(p.lda) * 2, uint64_t(p.lda) * 2 * uint64_t(p.M), uint64_t(p.lda) * 2 * uint64_t(p.M)};
@@ -647,7 +727,7 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
     if (int rc = make_map(&ma, p.dtype, p.a, 4, dims, strides, box, ones)) return rc;
     const uint64_t bdims[3] = {uint64_t(p.K), uint64_t(p.N), 1};
     const uint64_t bstr[2] = {uint64_t(p.ldb) * 2, uint64_t(p.ldb) * 2 * uint64_t(p.N)};
-    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn), 1};
+    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn / cl), 1};
     if (int rc = make_map(&mb, p.dtype, p.b, 3, bdims, bstr, bbox, ones)) return rc;
   }
   if (prm.k_iters2) {
@@ -657,16 +737,16 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
     if (int rc = make_map(&ma2, p.dtype, p.a2, 4, dims, strides, box, ones)) return rc;
     const uint64_t bdims[3] = {uint64_t(p.K2), uint64_t(p.N), 1};
     const uint64_t bstr[2] = {uint64_t(p.ldb2) * 2, uint64_t(p.ldb2) * 2 * uint64_t(p.N)};
-    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn), 1};
+    const uint32_t bbox[3] = {uint32_t(BK), uint32_t(bn / cl), 1};
     if (int rc = make_map(&mb2, p.dtype, p.b2, 3, bdims, bstr, bbox, ones)) return rc;
   } else {
     ma2 = ma; mb2 = mb;
   }
   prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   const bool bf = p.dtype == RB200_BF16;
-  if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm);
-  if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm);
-  return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm);
+  if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm, cl);
+  if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm, cl);
+  return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm, cl);
 }
 
 }  // namespace rb200

@@ -132,3 +132,94 @@ def try_fuse_sum(chain: Any, inputs: tuple[Any, ...]) -> Any:
         if out is not NotImplemented:
             return out
     return NotImplemented
+
+
+# -- tail residual ------------------------------------------------------------------------------
+def forward_with_residual(chain: Any, args: tuple[Any, ...], residual: Tensor) -> Any:
+    """``chain(*args) + residual`` with the addition folded into the epilogue of the chain's final
+    GEMM when the tail is (nested plain Chains ending in) a Linear or a fusable LoraAdapter.
+    Always returns the sum (falls back to a separate add kernel)."""
+    from refiners_b200.fluxion.layers.graph import Chain
+    from refiners_b200.fluxion.layers.leaves import Linear
+
+    steps = chain._steps()
+    fused: Any = NotImplemented
+    if steps and steps[-1][0] == "call" and B.fusion_enabled():
+        name, last = steps[-1][1], steps[-1][2]
+        h = run_steps(chain, steps[:-1], args) if len(steps) > 1 else (args[0] if len(args) == 1 else args)
+        hargs = h if isinstance(h, tuple) else (h,)
+        if type(last) is Linear and not _hooked(last) and len(hargs) == 1 and isinstance(hargs[0], Tensor):
+            t = hargs[0]
+            if t.is_cuda and t.shape[:-1] == residual.shape[:-1] and last.out_features == residual.shape[-1] and t.dtype == residual.dtype:
+                fused = chain._call_fused(name, lambda u: B.linear(u, last.weight, last.bias, residual=residual), t)
+        elif isinstance(last, Chain) and type(last).forward is Chain.forward and not _hooked(last):
+            fused = chain._call_fused(name, lambda *u: forward_with_residual(last, u, residual), *hargs)
+        elif hasattr(last, "_forward_with_residual") and not _hooked(last):
+            fused = chain._call_fused(name, lambda *u: last._forward_with_residual(u, residual), *hargs)
+        if fused is NotImplemented:
+            out = chain._call_layer(last, name, *hargs)
+        else:
+            chain._reset_context()
+            return fused
+    else:
+        out = run_steps(chain, steps, args)
+    chain._reset_context()
+    if isinstance(out, Tensor) and out.is_cuda and out.shape == residual.shape and out.dtype == residual.dtype:
+        return B.add(out, residual)
+    return out + residual
+
+
+# -- Distribute: sibling Linears fed the same tensor become one GEMM -----------------------------------
+def _same_tensor(a: Any, b: Any) -> bool:
+    return (
+        isinstance(a, Tensor)
+        and isinstance(b, Tensor)
+        and (a is b or (a.data_ptr() == b.data_ptr() and a.shape == b.shape and a.stride() == b.stride() and a.dtype == b.dtype))
+    )
+
+
+def try_fuse_distribute(chain: Any, args: tuple[Any, ...]) -> Any:
+    """Distribute(Linear, Linear, ...)(x, x, ...) -> one GEMM over the row-concatenated weights for
+    every run of children that are plain Linears receiving the same tensor (self-attention q/k/v,
+    cross-attention k/v).  Outputs are column views of the fused result."""
+    from refiners_b200.fluxion.layers.leaves import Linear
+
+    if not B.fusion_enabled():
+        return NotImplemented
+    items = list(chain._modules.items())
+    if len(items) != len(args) or len(items) < 2:
+        return NotImplemented
+    n = len(items)
+    runs: list[tuple[int, int]] = []
+    i = 0
+    while i < n:
+        j = i + 1
+        lin = items[i][1]
+        if type(lin) is Linear and isinstance(args[i], Tensor) and args[i].is_cuda and not _hooked(lin):
+            while (
+                j < n
+                and type(items[j][1]) is Linear
+                and not _hooked(items[j][1])
+                and _same_tensor(args[i], args[j])
+                and items[j][1].in_features == lin.in_features
+                and (items[j][1].bias is None) == (lin.bias is None)
+                and items[j][1].weight.dtype == lin.weight.dtype
+            ):
+                j += 1
+        runs.append((i, j))
+        i = j
+    if all(j - i == 1 for i, j in runs):
+        return NotImplemented
+    outs: list[Any] = [None] * n
+    for i, j in runs:
+        if j - i == 1:
+            outs[i] = chain._call_layer(items[i][1], items[i][0], args[i])
+            continue
+        group = [items[k][1] for k in range(i, j)]
+        w, b = B.concat_linear_weights([m.weight for m in group], [m.bias for m in group])
+        y = chain._call_fused(items[i][0], lambda x, w=w, b=b: B.linear(x, w, b), args[i])
+        off = 0
+        for k, m in zip(range(i, j), group):
+            outs[k] = y[..., off : off + m.out_features]
+            off += m.out_features
+    return tuple(outs)

@@ -314,12 +314,23 @@ class LoraAdapter(fl.Sum, Adapter[fl.WeightedModule]):
             triples.append((down.weight, up.weight, float(mul.scale)))
         return triples
 
-    def forward(self, *inputs: Any) -> Any:
+    def _forward_with_residual(self, inputs: tuple[Any, ...], residual: Tensor | None) -> Any:
+        """One-launch evaluation (optionally adding a skip connection); NotImplemented if the
+        adapter's current children do not allow it."""
         if len(inputs) == 1 and isinstance(inputs[0], Tensor) and inputs[0].is_cuda and B.fusion_enabled():
+            x = inputs[0]
             triples = self._fusable()
-            if triples is not None and B.lora_fusable(inputs[0], triples):
+            if triples is not None and B.lora_fusable(x, triples):
                 base = cast(fl.Linear, self[0])
-                return B.linear(inputs[0], base.weight, base.bias, loras=triples)
+                if residual is not None and (x.shape[:-1] != residual.shape[:-1] or base.out_features != residual.shape[-1]):
+                    return NotImplemented
+                return B.linear(x, base.weight, base.bias, loras=triples, residual=residual)
+        return NotImplemented
+
+    def forward(self, *inputs: Any) -> Any:
+        fused = self._forward_with_residual(inputs, None)
+        if fused is not NotImplemented:
+            return fused
         return fl.Sum.forward(self, *inputs)
 
 

@@ -481,6 +481,12 @@ class Distribute(Chain):
     def forward(self, *args: Any) -> tuple[Any, ...]:
         n, m = len(args), len(self._modules)
         assert n == m, f"Number of positional arguments ({n}) must match number of sub-modules ({m})."
+        if n > 1 and isinstance(args[0], Tensor) and args[0].is_cuda:
+            from refiners_b200.engine import fusion
+
+            fused = fusion.try_fuse_distribute(self, args)
+            if fused is not NotImplemented:
+                return fused
         return tuple(self._call_layer(layer, name, arg) for arg, (name, layer) in zip(args, self._modules.items()))
 
     def _show_only_tag(self) -> bool:
@@ -539,25 +545,11 @@ class Residual(Chain):
         assert len(inputs) == 1, "Residual connection can only be used with a single input."
         x = inputs[0]
         if isinstance(x, Tensor) and x.is_cuda:
-            from refiners_b200 import backend as B
             from refiners_b200.engine import fusion
 
-            last = fusion.tail_linear(self) if B.fusion_enabled() else None
-            if last is not None and self._steps()[-1][0] == "call":
-                # the final GEMM adds the skip connection in its epilogue (fp32, one launch)
-                h = self._run_children(inputs, skip_last=True)
-                if isinstance(h, Tensor) and h.shape[:-1] == x.shape[:-1] and last.out_features == x.shape[-1]:
-                    name = next(reversed(self._modules))
-                    out = self._call_fused(name, lambda t: B.linear(t, last.weight, last.bias, residual=x), h)
-                    self._reset_context()
-                    return out
-                out = self._call_layer(last, next(reversed(self._modules)), *(h if isinstance(h, tuple) else (h,)))
-                self._reset_context()
-                return B.add(out, x) if out.shape == x.shape and out.dtype == x.dtype else out + x
-            out = Chain.forward(self, *inputs)
-            if isinstance(out, Tensor) and out.shape == x.shape and out.dtype == x.dtype and out.is_cuda:
-                return B.add(out, x)
-            return out + x
+            # the skip connection is added in the epilogue of the chain's final GEMM when the tail is
+            # a Linear (possibly nested in plain Chains), else by one add kernel
+            return fusion.forward_with_residual(self, inputs, x)
         return Chain.forward(self, *inputs) + x
 
 
