@@ -294,6 +294,8 @@ def run_gpu_arm(args) -> None:
         gpu_launches = eager_launches + graph_launches
 
         log(f'resident loop done: {ms_total / args.steps:.2f} ms/step')
+        if args.resident_only:
+            return
         # end to end: host buffers in, host result out, every step
         for s in range(3):
             step_e2e(s)
@@ -367,6 +369,7 @@ def main() -> None:
     ap.add_argument("--latent-batch", type=int, default=LATENT_BATCH)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-only", action="store_true", help="stress mode: skip the e2e loop and the extras")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

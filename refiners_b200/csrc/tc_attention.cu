@@ -17,6 +17,9 @@
 // The Sq x Sk score matrix never exists in memory.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rb200 {
@@ -42,6 +45,7 @@ struct AttnParams {
   float scale_log2e;
   float scale2;
   uint32_t idesc_qk, idesc_pv;
+  int early_s;  // 1: issue S_{j+1} before P_j V_j (pipelined); 0: strictly after (debug)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -65,9 +69,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("rb200 sdpa: mbarrier wait timed out: tag=%d parity=%u block=%d thread=%d\n", tag, parity, int(blockIdx.x), int(threadIdx.x));
+  __trap();
+}
+// Bounded wait: a protocol bug reports which barrier starved and traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();  // protocol bug: fail loudly instead of hanging the GPU
+    if (spin > (1u << 26)) mbar_timeout(tag, parity);
   }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -146,7 +155,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + STAGES * K_BYTES;
   uint8_t* sP = sV + STAGES * V_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);  // after BOTH P buffers
   uint64_t* kv_full = bars;              // [STAGES]
   uint64_t* kv_empty = bars + STAGES;    // [STAGES]
   uint64_t* q_full = bars + 2 * STAGES;
@@ -197,7 +206,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int qt = int(w % p.n_qt);
         const int h = int((w / p.n_qt) % p.H);
         const int b = int(w / (int64_t(p.n_qt) * p.H));
-        mbar_wait(q_empty, qphase ^ 1);
+        mbar_wait(q_empty, qphase ^ 1, 1);
         mbar_arrive_expect_tx(q_full, Q_BYTES);
         tma_load_4d(sQ, &map_q, q_full, 0, h, qt * QT, b);
         qphase ^= 1;
@@ -205,7 +214,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const int64_t Sk = set ? p.Sk2 : p.Sk;
           const int ntiles = int((Sk + KT - 1) / KT);
           for (int j = 0; j < ntiles; ++j) {
-            mbar_wait(&kv_empty[stage], phase ^ 1);
+            mbar_wait(&kv_empty[stage], phase ^ 1, 2);
             mbar_arrive_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
             tma_load_4d(sK + stage * K_BYTES, set ? &map_k2 : &map_k, &kv_full[stage], 0, h, j * KT, b);
             tma_load_4d(sV + stage * V_BYTES, set ? &map_v2 : &map_v, &kv_full[stage], 0, h, j * KT, b);
@@ -226,8 +235,8 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       const uint64_t dq = desc_kmajor(smem_u32(sQ));
       auto issue_s = [&](uint32_t gt) {
         const uint32_t b = gt & 1, k_use = gt >> 1;
-        mbar_wait(&kv_full[st_s], ph_s);
-        mbar_wait(&bar_sfree[b], (k_use & 1) ^ 1);  // previous S in this buffer has been read
+        mbar_wait(&kv_full[st_s], ph_s, 3);
+        mbar_wait(&bar_sfree[b], (k_use & 1) ^ 1, 4);  // previous S in this buffer has been read
         tcgen05_fence_after();
         const uint64_t dk = desc_kmajor(smem_u32(sK + st_s * K_BYTES));
 #pragma unroll
@@ -239,7 +248,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
       };
       for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        mbar_wait(q_full, qphase);
+        mbar_wait(q_full, qphase, 5);
         qphase ^= 1;
         tcgen05_fence_after();
         for (int set = 0; set < nsets; ++set) {
@@ -247,9 +256,9 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           const int ntiles = int((Sk + KT - 1) / KT);
           issue_s(g);
           for (int j = 0; j < ntiles; ++j, ++g) {
-            if (j + 1 < ntiles) issue_s(g + 1);  // S_{j+1} runs while the softmax warps work on S_j
+            if (p.early_s && j + 1 < ntiles) issue_s(g + 1);  // S_{j+1} runs while the softmax warps work on S_j
             const uint32_t b = g & 1;
-            mbar_wait(&bar_p[b], (g >> 1) & 1);  // P_j in smem buffer b; O buffer b has been drained
+            mbar_wait(&bar_p[b], (g >> 1) & 1, 6);  // P_j in smem buffer b; O buffer b has been drained
             tcgen05_fence_after();
             const uint64_t dp = desc_kmajor(smem_u32(sP + b * P_BYTES));
             const uint64_t dv = desc_mnmajor(smem_u32(sV + st_pv * V_BYTES), V_BYTES);
@@ -261,6 +270,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             umma_commit(&kv_empty[st_pv]);  // K_j / V_j slot free once these MMAs retire
             umma_commit(&bar_o[b]);
             if (++st_pv == STAGES) st_pv = 0;
+            if (!p.early_s && j + 1 < ntiles) issue_s(g + 1);
           }
         }
         umma_commit(q_empty);  // every MMA reading Q has been issued; the slot frees when they retire
@@ -293,7 +303,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < ntiles; ++j, ++g) {
           const uint32_t buf = g & 1;
-          mbar_wait(&bar_s[buf], (g >> 1) & 1);
+          mbar_wait(&bar_s[buf], (g >> 1) & 1, 7);
           tcgen05_fence_after();
           float s[KT];
           {
@@ -336,7 +346,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           if (j > 0) {
             // O_{j-1} = P_{j-1} V_{j-1} landed long ago: fold it in, then rescale to the new maximum
             const uint32_t gp = g - 1, bp = gp & 1;
-            mbar_wait(&bar_o[bp], (gp >> 1) & 1);
+            mbar_wait(&bar_o[bp], (gp >> 1) & 1, 8);
             tcgen05_fence_after();
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -362,7 +372,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         // last tile of the set
         {
           const uint32_t gp = g - 1, bp = gp & 1;
-          mbar_wait(&bar_o[bp], (gp >> 1) & 1);
+          mbar_wait(&bar_o[bp], (gp >> 1) & 1, 9);
           tcgen05_fence_after();
           const float wgt = (set ? p.scale2 : 1.f) * (l_run > 0.f ? 1.f / l_run : 0.f);
 #pragma unroll
@@ -500,6 +510,11 @@ int tc_sdpa(cudaStream_t st, const SdpaProblem& p) {
   prm.scale2 = p.scale2;
   const uint32_t fmt = p.dtype == RB200_BF16 ? 1u : 0u;
   const uint32_t common = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(64 >> 3) << 17) | (uint32_t(QT >> 4) << 24);
+  static const int early = [] {
+    const char* e = getenv("RB200_ATTN_PIPE");
+    return e ? atoi(e) : 1;
+  }();
+  prm.early_s = early;
   prm.idesc_qk = common;               // A, B K-major
   prm.idesc_pv = common | (1u << 16);  // B (= V) MN-major
   if (p.dtype == RB200_BF16)

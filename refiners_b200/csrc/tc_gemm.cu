@@ -17,6 +17,8 @@
 // An optional second K segment (A2, B2) appends extra K blocks; LoRA up-projections use it.
 #include <cuda.h>
 
+#include <cstdio>
+
 #include <cstdlib>
 
 #include "common.cuh"
@@ -78,9 +80,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("rb200 gemm: mbarrier wait timed out: tag=%d parity=%u block=%d thread=%d\n", tag, parity, int(blockIdx.x), int(threadIdx.x));
+  __trap();
+}
+// Bounded wait: a protocol bug reports which barrier starved and traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 26)) mbar_timeout(tag, parity);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -295,7 +302,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int n0 = nt * BN;
         int tap = 0, kb = 0;
         for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           void* da = smem_a + size_t(stage) * A_BYTES;
           void* db = smem_b + size_t(stage) * B_BYTES;
@@ -338,11 +345,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int grp = cluster_id; grp < num_groups; grp += num_clusters) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + uint32_t(acc * BN);
         for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase, 3);
           tcgen05_fence_after();
           const uint64_t da = make_sw128_desc(smem_u32(smem_a + size_t(stage) * A_BYTES));
           const uint64_t db = make_sw128_desc(smem_u32(smem_b + size_t(stage) * B_BYTES));
@@ -396,7 +403,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         m_lin = int64_t(mt) * BM + row;
         valid = m_lin < p.M;
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(lg * 32) << 16);
 #pragma unroll 1
