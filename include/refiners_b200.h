@@ -119,8 +119,8 @@ int rb200_conv2d(void* stream, int dtype, const void* x, const void* w_packed, c
 /* ---- GroupNorm (+SiLU) ----------------------------------------------------------------------
  * Replaces fluxion/layers/norm.py:52-92 (+ activations.py:31-41 when silu != 0).
  * x, y: NHWC [B, HW, C]; statistics per (sample, group) over HW * C/G elements in fp32.
- * ws: rb200_group_norm_workspace_bytes(B, HW, C) bytes. */
-size_t rb200_group_norm_workspace_bytes(int64_t B, int64_t HW, int64_t C);
+ * ws: rb200_group_norm_workspace_bytes(B, HW, G) bytes. */
+size_t rb200_group_norm_workspace_bytes(int64_t B, int64_t HW, int G);
 int rb200_group_norm(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t HW,
                      int64_t C, int G, float eps, const void* gamma, const void* beta, int silu,
                      void* ws, size_t ws_bytes);

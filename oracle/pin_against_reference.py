@@ -48,6 +48,22 @@ def _close(name: str, got: torch.Tensor, want: torch.Tensor, rel: float = 1e-5) 
         raise SystemExit(f"oracle disagrees with the reference on {name}")
 
 
+def control_lora_test_weights() -> dict[str, torch.Tensor]:
+    """A small synthetic ControlLora checkpoint (shape conventions of control_lora.py:319-411): rank-4
+    LoRAs on three shared leaves; zero-convs and the condition encoder keep their (keyed) weights."""
+    gen = torch.Generator().manual_seed(99)
+    targets = {
+        "DownBlocks.Chain_5.SDXLCrossAttention.Chain_2.CrossAttentionBlock_1.Residual_1.SelfAttention.Distribute.Linear_1": (640, 640),
+        "DownBlocks.Chain_8.SDXLCrossAttention.Chain_2.CrossAttentionBlock_3.Residual_3.Linear_2": (5120, 1280),
+        "MiddleBlock.SDXLCrossAttention.Chain_1.Linear": (1280, 1280),
+    }
+    sd: dict[str, torch.Tensor] = {}
+    for path, (fin, fout) in targets.items():
+        sd[f"ControlLora.{path}.down"] = torch.randn(4, fin, generator=gen) * 0.25
+        sd[f"ControlLora.{path}.up"] = torch.randn(fout, 4, generator=gen) * 0.05
+    return sd
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -205,6 +221,25 @@ def main(write: bool) -> None:
         fx.update({"sdxl.x": x, "sdxl.timestep": ts, "sdxl.ctx": ctx, "sdxl.pooled": pooled, "sdxl.time_ids": ids, "sdxl.y": y})
         _close("SDXLUNet", ounet.sdxl_unet(sdict, x, ts, ctx, pooled, ids), y)
         del unet, sdict
+        # SDXL + ControlLora (BASELINE config 4).  Not restated in the oracle: the fixture pins the
+        # refiners_b200 mirror directly against the reference's output.
+        from refiners.foundationals.latent_diffusion.stable_diffusion_xl.control_lora import ControlLoraAdapter
+
+        unet = SDXLUNet(4)
+        adapter = ControlLoraAdapter("canny", unet, scale=0.8).inject()
+        lora_sd = control_lora_test_weights()
+        ControlLoraAdapter.load_lora_layers("canny", lora_sd, adapter.control_lora)  # zero-convs / encoder keep keyed weights
+        shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        unet.load_state_dict(keyed_state_dict(shapes, seed=3))
+        x, ts = g(2, 4, 32, 32), torch.tensor([981.0])
+        ctx, pooled, cond = g(2, 77, 2048), g(2, 1280), torch.rand(2, 3, 256, 256)
+        ids = torch.tensor([[1024, 1024, 0, 0, 1024, 1024]]).repeat(2, 1)
+        unet.set_timestep(ts); unet.set_clip_text_embedding(ctx); unet.set_pooled_text_embedding(pooled); unet.set_time_ids(ids)
+        adapter.set_condition(cond)
+        y = unet(x)
+        fx.update({"cl.x": x, "cl.timestep": ts, "cl.ctx": ctx, "cl.pooled": pooled, "cl.time_ids": ids, "cl.cond": cond, "cl.y": y})
+        print(f"  [ref ] SDXLUNet + ControlLora: output max {y.abs().max().item():.3f} (fixture only)")
+        del unet, adapter
         out["unets"] = fx
 
         # ------------------------------------------------------------------------ SAM

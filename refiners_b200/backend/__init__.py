@@ -70,7 +70,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_geglu_pack": (_I, [_P, _I, _P, _P, _P, _P, _L, _L]),
     "rb200_conv2d_pack_weight": (_I, [_P, _I, _P, _P, _L, _L, _I, _I]),
     "rb200_conv2d": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I]),
-    "rb200_group_norm_workspace_bytes": (_Z, [_L, _L, _L]),
+    "rb200_group_norm_workspace_bytes": (_Z, [_L, _L, _I]),
     "rb200_group_norm": (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _F, _P, _P, _I, _P, _Z]),
     "rb200_layer_norm": (_I, [_P, _I, _P, _P, _L, _L, _F, _P, _P]),
     "rb200_unary": (_I, [_P, _I, _P, _P, _L, _I]),
@@ -319,7 +319,7 @@ def _group_norm_impl(x: Tensor, groups: int, gamma: Tensor, beta: Tensor, eps: f
         yk = torch.empty_like(xk)
         HW = xk.shape[1]
         y = None
-    ws_bytes = lib.rb200_group_norm_workspace_bytes(B, HW, C)
+    ws_bytes = lib.rb200_group_norm_workspace_bytes(B, HW, groups)
     ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
     if xk.numel():
         _check(

@@ -165,10 +165,7 @@ int rb200_conv2d(void* stream, int dtype, const void* x, const void* w_packed, c
   return run_gemm(st, p);
 }
 
-size_t rb200_group_norm_workspace_bytes(int64_t B, int64_t HW, int64_t C) {
-  // upper bound over the group count (G <= C)
-  return group_norm_ws(B, HW, int(C < 1024 ? C : 1024));
-}
+size_t rb200_group_norm_workspace_bytes(int64_t B, int64_t HW, int G) { return group_norm_ws(B, HW, G) + 256; }
 
 int rb200_group_norm(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G, float eps,
                      const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes) {

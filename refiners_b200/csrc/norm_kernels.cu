@@ -8,11 +8,16 @@ namespace rb200 {
 namespace {
 
 // ------------------------------------------------------------------------------ GroupNorm
-constexpr int GN_PIX = 128;  // pixels per block
+// pixels per block: small enough that B * ceil(HW / pix) blocks fill the 148 SMs several times over
+inline int gn_pix(int64_t B, int64_t HW) {
+  int pix = 128;
+  while (pix > 8 && B * ceil_div(HW, pix) < int64_t(sm_count()) * 6) pix >>= 1;
+  return pix;
+}
 
 template <typename T, int V>
 __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ part, int64_t HW, int C, int G,
-                                  int chunks) {
+                                  int chunks, int GN_PIX) {
   extern __shared__ float sm[];  // [lanes][C][2]
   const int CV = C / V;
   const int v = threadIdx.x, lane = threadIdx.y, lanes = blockDim.y;
@@ -60,10 +65,37 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
   (void)CV;
 }
 
+// one warp per (sample, group): fixed-order fp64 combination of the per-chunk partial sums
+__global__ void gn_finalize_kernel(const float* __restrict__ part, float* __restrict__ stats, int64_t HW, int C, int G,
+                                   int chunks, float eps, int total) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= total) return;
+  const int b = gw / G, g = gw - b * G;
+  const float* src = part + (int64_t(b) * chunks * G + g) * 2;
+  double ss = 0.0, qq = 0.0;
+  for (int c = lane; c < chunks; c += 32) {
+    ss += double(src[int64_t(c) * G * 2 + 0]);
+    qq += double(src[int64_t(c) * G * 2 + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  }
+  if (lane == 0) {
+    const double n = double(HW) * double(C / G);
+    const double mean = ss / n;
+    double var = qq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(int64_t(b) * G + g) * 2 + 0] = float(mean);
+    stats[(int64_t(b) * G + g) * 2 + 1] = float(1.0 / sqrt(var + double(eps)));
+  }
+}
+
 template <typename T, int V>
-__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ part,
+__global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
                                 const T* __restrict__ gamma, const T* __restrict__ beta, int64_t HW, int C, int G,
-                                int chunks, float eps, int silu) {
+                                int GN_PIX, int silu) {
   extern __shared__ float sm[];  // mean[G], rstd[G]
   const int v = threadIdx.x, lane = threadIdx.y, lanes = blockDim.y;
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -71,18 +103,8 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
   const int nthreads = blockDim.x * blockDim.y;
   const int cpg = C / G;
   for (int g = t; g < G; g += nthreads) {
-    double ss = 0.0, qq = 0.0;
-    const float* src = part + (int64_t(b) * chunks * G + g) * 2;
-    for (int c = 0; c < chunks; ++c) {
-      ss += double(src[int64_t(c) * G * 2 + 0]);
-      qq += double(src[int64_t(c) * G * 2 + 1]);
-    }
-    const double n = double(HW) * double(cpg);
-    const double mean = ss / n;
-    double var = qq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sm[g] = float(mean);
-    sm[G + g] = float(1.0 / sqrt(var + double(eps)));
+    sm[g] = stats[(int64_t(b) * G + g) * 2 + 0];
+    sm[G + g] = stats[(int64_t(b) * G + g) * 2 + 1];
   }
   __syncthreads();
   float ga[V], be[V], mu[V], rs[V];
@@ -125,18 +147,23 @@ int gn_launch(cudaStream_t st, const T* x, T* y, int64_t B, int64_t HW, int C, i
               const T* beta, int silu, float* part) {
   const int CV = C / V;
   if (CV > 1024) RB200_FAIL(-1, "group_norm: C=%d too wide for this layout", C);
+  const int pix = gn_pix(B, HW);
   int lanes = 256 / CV;
   if (lanes < 1) lanes = 1;
-  if (lanes > GN_PIX) lanes = GN_PIX;
+  if (lanes > pix) lanes = pix;
   while (CV * lanes < G) ++lanes;  // need at least G threads for the group reduce
-  const int chunks = int(ceil_div(HW, GN_PIX));
+  const int chunks = int(ceil_div(HW, pix));
   dim3 block(CV, lanes), grid(chunks, (unsigned)B);
   const size_t sm1 = size_t(lanes) * C * 2 * sizeof(float);
   if (sm1 > 200 * 1024) RB200_FAIL(-1, "group_norm: shared memory need %zu too large", sm1);
   if (sm1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm1));
-  gn_partial_kernel<T, V><<<grid, block, sm1, st>>>(x, part, HW, C, G, chunks);
+  float* stats = part + size_t(B) * chunks * G * 2;
+  gn_partial_kernel<T, V><<<grid, block, sm1, st>>>(x, part, HW, C, G, chunks, pix);
   RB200_CHECK_LAUNCH("gn_partial");
-  gn_apply_kernel<T, V><<<grid, block, 2 * G * sizeof(float), st>>>(x, y, part, gamma, beta, HW, C, G, chunks, eps, silu);
+  const int total = int(B) * G;
+  gn_finalize_kernel<<<unsigned(ceil_div(int64_t(total) * 32, 256)), 256, 0, st>>>(part, stats, HW, C, G, chunks, eps, total);
+  RB200_CHECK_LAUNCH("gn_finalize");
+  gn_apply_kernel<T, V><<<grid, block, 2 * G * sizeof(float), st>>>(x, y, stats, gamma, beta, HW, C, G, pix, silu);
   RB200_CHECK_LAUNCH("gn_apply");
   return 0;
 }
@@ -200,6 +227,69 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x
   } else {
     for (int c = lane; c < C; c += 32) yr[c] = from_f<T>((to_f(xr[c]) - mean) * rstd * to_f(gamma[c]) + to_f(beta[c]));
   }
+}
+
+// Row kept in registers: one global read, two reductions, one write (VPL 16-byte vectors per lane).
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) layer_norm_reg_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int C,
+                                                             float eps, const T* __restrict__ gamma,
+                                                             const T* __restrict__ beta) {
+  constexpr int V = 16 / sizeof(T);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const T* xr = x + row * C;
+  T* yr = y + row * C;
+  const int nvec = C / V;
+  Vec16<T> r[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      r[i] = ld16(xr + vi * V);
+#pragma unroll
+      for (int e = 0; e < V; ++e) s += to_f(r[i].v[e]);
+    }
+  }
+  const float mean = warp_sum(s) / float(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float d = to_f(r[i].v[e]) - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(C) + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const Vec16<T> g = ld16(gamma + vi * V), bt = ld16(beta + vi * V);
+      Vec16<T> o;
+#pragma unroll
+      for (int e = 0; e < V; ++e) o.v[e] = from_f<T>((to_f(r[i].v[e]) - mean) * rstd * to_f(g.v[e]) + to_f(bt.v[e]));
+      st16(yr + vi * V, o);
+    }
+  }
+}
+
+template <typename T>
+void ln_launch(cudaStream_t st, unsigned grid, int warps, const T* x, T* y, int64_t rows, int C, float eps, const T* gamma,
+               const T* beta, int vec_ok) {
+  constexpr int V = 16 / sizeof(T);
+  const int vpl = vec_ok ? int(ceil_div(C / V, 32)) : 99;
+  const int threads = warps * 32;
+  if (vpl <= 1) layer_norm_reg_kernel<T, 1><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta);
+  else if (vpl == 2) layer_norm_reg_kernel<T, 2><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta);
+  else if (vpl == 3) layer_norm_reg_kernel<T, 3><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta);
+  else if (vpl <= 5) layer_norm_reg_kernel<T, 5><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta);
+  else if (vpl <= 8) layer_norm_reg_kernel<T, 8><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta);
+  else layer_norm_kernel<T><<<grid, threads, 0, st>>>(x, y, rows, C, eps, gamma, beta, vec_ok);
 }
 
 // ---------------------------------------------------------------------------- elementwise
@@ -374,17 +464,22 @@ inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 1
     default: RB200_FAIL(-1, "bad dtype %d", dtype);                        \
   }
 
+size_t group_norm_ws(int64_t B, int64_t HW, int G);
+
 int group_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G,
                     float eps, const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes) {
   if (G <= 0 || C % G != 0) RB200_FAIL(-1, "group_norm: C=%lld not divisible by G=%d", (long long)C, G);
-  const size_t need = size_t(B) * size_t(ceil_div(HW, GN_PIX)) * size_t(G) * 2 * sizeof(float);
+  const size_t need = group_norm_ws(B, HW, G);
   if (ws_bytes < need || ws == nullptr) RB200_FAIL(-1, "group_norm: workspace %zu < %zu", ws_bytes, need);
   if (B > 65535) RB200_FAIL(-1, "group_norm: batch %lld too large", (long long)B);
   DISPATCH_T(dtype, return gn_dispatch<T>(st, x, y, B, HW, C, G, eps, gamma, beta, silu, static_cast<float*>(ws)));
   return 0;
 }
 
-size_t group_norm_ws(int64_t B, int64_t HW, int G) { return size_t(B) * size_t(ceil_div(HW, GN_PIX)) * size_t(G) * 2 * sizeof(float); }
+size_t group_norm_ws(int64_t B, int64_t HW, int G) {
+  // per-chunk partial sums + final (mean, rstd) per (sample, group)
+  return (size_t(B) * size_t(ceil_div(HW, gn_pix(B, HW))) + size_t(B)) * size_t(G) * 2 * sizeof(float);
+}
 
 int layer_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows, int64_t C, float eps,
                     const void* gamma, const void* beta) {
@@ -393,7 +488,7 @@ int layer_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t 
   DISPATCH_T(dtype, {
     constexpr int V = 16 / sizeof(T);
     const int vec_ok = (C % V == 0) && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta);
-    layer_norm_kernel<T><<<grid, warps * 32, 0, st>>>((const T*)x, (T*)y, rows, int(C), eps, (const T*)gamma, (const T*)beta, vec_ok);
+    ln_launch<T>(st, grid, warps, (const T*)x, (T*)y, rows, int(C), eps, (const T*)gamma, (const T*)beta, vec_ok);
   });
   RB200_CHECK_LAUNCH("layer_norm");
   return 0;

@@ -141,6 +141,49 @@ def test_sdxl_unet_host():
     check(run_sdxl(unet, f, "cpu", torch.float32), f["sdxl.y"], "host")
 
 
+def load_control_lora_unet(device="cpu", dtype=torch.float32):
+    """SDXLUNet + ControlLoraAdapter('canny') + the synthetic LoRA checkpoint, keyed weights (seed 3) -
+    the construction recorded by oracle/pin_against_reference.py."""
+    from oracle.pin_against_reference import control_lora_test_weights
+    from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.control_lora import ControlLoraAdapter
+
+    def build():
+        unet = SDXLUNet(4, device="meta")
+        adapter = ControlLoraAdapter("canny", unet, scale=0.8).inject()
+        ControlLoraAdapter.load_lora_layers("canny", control_lora_test_weights(), adapter.control_lora)
+        return unet, adapter
+
+    unet, adapter = build()
+    shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    sd = keyed_state_dict(shapes, seed=3)
+    # shared leaves appear under two keys (UNet path and ControlLora path); like load_state_dict on real
+    # tensors, the LAST key in state-dict order provides the value of the shared storage
+    final: dict[int, torch.Tensor] = {}
+    params = dict(unet.state_dict(keep_vars=True))
+    for k in shapes:
+        final[id(params[k])] = sd[k]
+    unet.load_state_dict({k: final[id(params[k])].to(device, dtype) for k in shapes}, assign=True)
+    return unet, adapter
+
+
+def run_control_lora(unet, adapter, f, device, dtype):
+    unet.set_timestep(f["cl.timestep"].to(device))
+    unet.set_clip_text_embedding(f["cl.ctx"].to(device, dtype))
+    unet.set_pooled_text_embedding(f["cl.pooled"].to(device, dtype))
+    unet.set_time_ids(f["cl.time_ids"].to(device))
+    adapter.set_condition(f["cl.cond"].to(device, dtype))
+    with no_grad():
+        return unet(f["cl.x"].to(device, dtype))
+
+
+def test_sdxl_control_lora_host():
+    """BASELINE config 4 graph (SDXL + ControlLora): shared leaves, LoRAs inside the control copy,
+    condition encoder, zero-convs accumulating into the UNet's residual slots."""
+    f = load_file(str(GOLDEN / "unets.safetensors"))
+    unet, adapter = load_control_lora_unet()
+    check(run_control_lora(unet, adapter, f, "cpu", torch.float32), f["cl.y"], "host")
+
+
 # ------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=str)
@@ -178,3 +221,11 @@ def test_sdxl_unet_gpu(cuda_device, dtype):
     y1 = run_sdxl(unet, f, cuda_device, dtype)
     check(y1, f["sdxl.y"], dtype)
     assert torch.equal(y1, run_sdxl(unet, f, cuda_device, dtype))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_sdxl_control_lora_gpu(cuda_device, dtype):
+    f = load_file(str(GOLDEN / "unets.safetensors"))
+    unet, adapter = load_control_lora_unet(device=cuda_device, dtype=dtype)
+    check(run_control_lora(unet, adapter, f, cuda_device, dtype), f["cl.y"], dtype)
