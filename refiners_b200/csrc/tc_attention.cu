@@ -7,11 +7,9 @@
 //   warp 0      TMA: K and V tiles [64 keys x 64] -> 128B-swizzled smem ring (3 stages); Q tile once
 //   warp 1      one thread issues  S = Q K^T  (UMMA 128x64x16, SS, K-major B)  -> TMEM S
 //                                  O_j = P V   (UMMA 128x64x16, SS, MN-major B) -> TMEM O
-//   warps 2..9  softmax: a query row (= TMEM lane) is shared by TWO threads, each owning 32 of the 64
-//               key columns of S and 32 of the 64 output columns of O (warps w and w+4 cover the same
-//               32 lanes); they exchange the row maximum through shared memory once per tile.
-//               tcgen05.ld S, online max / exp2 / sum in fp32, P -> bf16 -> swizzled smem (A operand of
-//               the second MMA); the running output is kept in registers: O = O * alpha + O_j.
+//   warps 2..5  softmax: thread = query row (TMEM lane): tcgen05.ld S, online max / exp2 / sum in
+//               fp32, P -> bf16 -> swizzled smem (the A operand of the second MMA), and the running
+//               output is kept in registers: O = O * alpha + O_j (tcgen05.ld of the 64-col O_j).
 // S, P and O_j are double buffered so that the tensor core computes S_{j+1} and O_j while the
 // softmax warps work on tile j: the softmax warps never wait for an MMA in steady state.
 // The [B, S, H*D] operands are addressed in place through 4D tensor maps (D, H, S, B): the head
@@ -31,10 +29,10 @@ constexpr int QT = 128;   // queries per tile (UMMA M)
 constexpr int KT = 64;    // keys per tile
 constexpr int HD = 64;    // head dim
 constexpr int STAGES = 3;
-constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (2 warps per 32-row lane group)
+constexpr int NUM_THREADS = 192;
 constexpr int Q_BYTES = QT * HD * 2, K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2, P_BYTES = QT * KT * 2;
 constexpr int TMEM_COLS = 256;  // S[2]: cols [0, 128), O[2]: cols [128, 256) - double buffered
-constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256 + 2 * 2 * QT * 4 + 2 * QT * 4;
+constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
 
 struct AttnParams {
   void* o;
@@ -167,8 +165,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* bar_p = q_full + 6;          // [2] P tile written to smem buffer b (previous O consumed)
   uint64_t* bar_o = q_full + 8;          // [2] O_j ready in TMEM buffer b (P buffer and V slot consumed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 10);
-  float* smax = reinterpret_cast<float*>(bars + 32);   // [2 tile parities][2 column halves][QT] row maxima
-  float* ssum = smax + 2 * 2 * QT;                      // [2 column halves][QT] row sums (end of a set)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsets = DUAL ? 2 : 1;
@@ -185,8 +181,8 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     mbar_init(q_empty, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_s[b], 1);
-      mbar_init(&bar_sfree[b], 8);
-      mbar_init(&bar_p[b], 8);
+      mbar_init(&bar_sfree[b], 4);
+      mbar_init(&bar_p[b], 4);
       mbar_init(&bar_o[b], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -282,68 +278,64 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
   } else {
     // ============================================================================ softmax
-    const int lg = warp & 3;                 // TMEM lane group this warp may access
-    const int ch = (warp - 2) >> 2;          // which half of the key columns / output columns
+    const int lg = warp & 3;
     const int row = lg * 32 + lane;
     const uint32_t lane_off = uint32_t(lg * 32) << 16;
-    constexpr int HC = KT / 2;               // 32 columns per thread
-    uint32_t g = 0;                          // global tile counter, in step with the MMA warp
+    uint32_t g = 0;  // global tile counter, in step with the MMA warp
     uint8_t* prow = sP + row * 128;
     const int sw = row & 7;
     T* obase = static_cast<T*>(p.o);
-    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + lg) : "memory"); };
     for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
       const int qt = int(w % p.n_qt);
       const int h = int((w / p.n_qt) % p.H);
       const int64_t b = w / (int64_t(p.n_qt) * p.H);
-      float out[DUAL ? HC : 1];
+      float out[DUAL ? HD : 1];
       if constexpr (DUAL) {
 #pragma unroll
-        for (int i = 0; i < HC; ++i) out[i] = 0.f;
+        for (int i = 0; i < HD; ++i) out[i] = 0.f;
       }
-      float acc[HC];
+      float acc[HD];
       for (int set = 0; set < nsets; ++set) {
         const int64_t Sk = set ? p.Sk2 : p.Sk;
         const int ntiles = int((Sk + KT - 1) / KT);
 #pragma unroll
-        for (int i = 0; i < HC; ++i) acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;   // l_run: sum over THIS thread's columns only
+        for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < ntiles; ++j, ++g) {
           const uint32_t buf = g & 1;
           mbar_wait(&bar_s[buf], (g >> 1) & 1, 7);
           tcgen05_fence_after();
-          float s[HC];
+          float s[KT];
           {
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_s + buf * 64 + lane_off + ch * HC, raw);
+            uint32_t raw0[32], raw1[32];
+            tmem_ld_32x32(tmem_s + buf * 64 + lane_off, raw0);
+            tmem_ld_32x32(tmem_s + buf * 64 + lane_off + 32, raw1);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < HC; ++i) s[i] = __uint_as_float(raw[i]);
+            for (int i = 0; i < 32; ++i) {
+              s[i] = __uint_as_float(raw0[i]);
+              s[32 + i] = __uint_as_float(raw1[i]);
+            }
           }
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_sfree[buf]);  // the tensor core may overwrite this S buffer
-          const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT) - ch * HC;
-          if (valid < HC) {
+          const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT);
+          if (valid < KT) {
 #pragma unroll
-            for (int i = 0; i < HC; ++i)
+            for (int i = 0; i < KT; ++i)
               if (i >= valid) s[i] = -INFINITY;
           }
           float tmax = s[0];
 #pragma unroll
-          for (int i = 1; i < HC; ++i) tmax = fmaxf(tmax, s[i]);
-          // row maximum over both column halves (partner thread = same lane of warp +-4)
-          float* mx = smax + (g & 1) * 2 * QT;
-          mx[ch * QT + row] = tmax;
-          pair_sync();
-          tmax = fmaxf(tmax, mx[(ch ^ 1) * QT + row]);
+          for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
           const float m_new = fmaxf(m_run, tmax);
           const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // exp2(-inf) = 0 on the first tile
           const float mb = m_new * p.scale_log2e;
           float psum = 0.f;
-          uint32_t packed[HC / 2];
+          uint32_t packed[KT / 2];
 #pragma unroll
-          for (int i = 0; i < HC; i += 2) {
+          for (int i = 0; i < KT; i += 2) {
             const float p0 = fast_exp2(fmaf(s[i], p.scale_log2e, -mb));
             const float p1 = fast_exp2(fmaf(s[i + 1], p.scale_log2e, -mb));
             psum += p0 + p1;
@@ -352,56 +344,58 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           l_run = l_run * alpha + psum;
           m_run = m_new;
           if (j > 0) {
-            // O_{j-1} = P_{j-1} V_{j-1} landed long ago: fold my 32 output columns in, then rescale
+            // O_{j-1} = P_{j-1} V_{j-1} landed long ago: fold it in, then rescale to the new maximum
             const uint32_t gp = g - 1, bp = gp & 1;
             mbar_wait(&bar_o[bp], (gp >> 1) & 1, 8);
             tcgen05_fence_after();
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_o + bp * 64 + lane_off + ch * HC, raw);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < HC; ++i) acc[i] = (acc[i] + __uint_as_float(raw[i])) * alpha;
+            for (int half = 0; half < 2; ++half) {
+              uint32_t raw[32];
+              tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[half * 32 + i] = (acc[half * 32 + i] + __uint_as_float(raw[i])) * alpha;
+            }
           }
-          // my 32 columns of P_j -> smem buffer (K-major, 128B swizzle).  The buffer was last read by
-          // PV_{j-2}, whose completion (bar_o) this thread has already observed.
+          // P_j -> smem buffer, K-major with the 128B swizzle the MMA descriptor expects.  The buffer
+          // was last read by PV_{j-2}, whose completion (bar_o) this thread has already observed.
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
             uint4 v = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-            *reinterpret_cast<uint4*>(prow + buf * P_BYTES + (((ch * 4 + c) ^ sw) << 4)) = v;
+            *reinterpret_cast<uint4*>(prow + buf * P_BYTES + ((c ^ sw) << 4)) = v;
           }
           fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_p[buf]);
         }
-        // end of the set: combine the two half-row sums, fold in the last O tile
-        ssum[ch * QT + row] = l_run;
-        pair_sync();
-        const float l_tot = l_run + ssum[(ch ^ 1) * QT + row];
-        pair_sync();  // partner has read my sum before the next set overwrites it
+        // last tile of the set
         {
           const uint32_t gp = g - 1, bp = gp & 1;
           mbar_wait(&bar_o[bp], (gp >> 1) & 1, 9);
           tcgen05_fence_after();
-          const float wgt = (set ? p.scale2 : 1.f) * (l_tot > 0.f ? 1.f / l_tot : 0.f);
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_o + bp * 64 + lane_off + ch * HC, raw);
-          tmem_ld_wait();
+          const float wgt = (set ? p.scale2 : 1.f) * (l_run > 0.f ? 1.f / l_run : 0.f);
 #pragma unroll
-          for (int i = 0; i < HC; ++i) {
-            const float v = wgt * (acc[i] + __uint_as_float(raw[i]));
-            if constexpr (DUAL) out[i] += v;
-            else acc[i] = v;
+          for (int half = 0; half < 2; ++half) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = wgt * (acc[half * 32 + i] + __uint_as_float(raw[i]));
+              if constexpr (DUAL) out[half * 32 + i] += v;
+              else acc[half * 32 + i] = v;
+            }
           }
         }
       }
       float* fin = DUAL ? out : acc;
       const int64_t qi = int64_t(qt) * QT + row;
       if (qi < p.Sq) {
-        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * HD + ch * HC;
+        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * HD;
         if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 8; ++c) {
             uint4 v;
             v.x = pack2<T>(fin[c * 8], fin[c * 8 + 1]);
             v.y = pack2<T>(fin[c * 8 + 2], fin[c * 8 + 3]);
@@ -411,7 +405,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < HC; ++i) dst[i] = from_f<T>(fin[i]);
+          for (int i = 0; i < HD; ++i) dst[i] = from_f<T>(fin[i]);
         }
       }
     }

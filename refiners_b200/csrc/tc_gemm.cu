@@ -213,6 +213,7 @@ __device__ __forceinline__ void add8(float* v, const T* p) {
 
 template <int BN> struct TileCfg;
 template <> struct TileCfg<256> { static constexpr int STAGES = 4; };
+template <> struct TileCfg<160> { static constexpr int STAGES = 5; };  // 320, 640, 1280 = k * 160 exactly
 template <> struct TileCfg<128> { static constexpr int STAGES = 6; };
 template <> struct TileCfg<64> { static constexpr int STAGES = 8; };
 
@@ -625,19 +626,26 @@ int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, con
 }
 
 int pick_bn(int64_t M_tiles, int64_t N) {
+  static const int forced = [] {
+    const char* e = getenv("RB200_GEMM_BN");  // experiments: force one tile width
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 256 || forced == 160 || forced == 128 || forced == 64) return forced;
   // fewest padded columns first, then fewest waves (bigger tiles amortise the A reads)
-  const int cands[3] = {256, 128, 64};
+  const int cands[4] = {256, 160, 128, 64};
   int best = 64;
   double best_cost = 1e300;
   const int sms = sm_count();
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     const int64_t tn = ceil_div(N, bn);
     const int64_t tiles = M_tiles * tn;
     const int64_t waves = ceil_div(tiles, sms);
     // time ~ waves * tile work; narrower tiles re-read A from smem more often per flop
     // (128 B/clk of operand traffic at BN=128 vs 96 at BN=256), hence the penalty factors
-    const double penalty = bn == 256 ? 1.0 : (bn == 128 ? 1.15 : 1.5);
+    // measured on B200 (profiles/r01_kernel_probes_bn.txt): the same work runs 1.3x / 1.45x slower with
+    // 160- / 128-wide tiles than with 256-wide ones (smem operand traffic 115 / 128 vs 96 B/clk)
+    const double penalty = bn == 256 ? 1.0 : (bn == 160 ? 1.3 : (bn == 128 ? 1.45 : 1.8));
     const double cost = double(waves) * (double(bn) * penalty + 24.0);
     if (cost < best_cost) {
       best_cost = cost;
@@ -715,6 +723,7 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
     prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
     const bool bf = p.dtype == RB200_BF16;
     if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm, cl);
+    if (bn == 160) return bf ? launch_tc<__nv_bfloat16, 160>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 160>(st, ma, mb, ma2, mb2, prm, cl);
     if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm, cl);
     return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm, cl);
   }
@@ -752,6 +761,7 @@ int tc_gemm(cudaStream_t st, const GemmProblem& p) {
   prm.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(bn >> 3) << 17) | (uint32_t(BM >> 4) << 24);
   const bool bf = p.dtype == RB200_BF16;
   if (bn == 256) return bf ? launch_tc<__nv_bfloat16, 256>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 256>(st, ma, mb, ma2, mb2, prm, cl);
+  if (bn == 160) return bf ? launch_tc<__nv_bfloat16, 160>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 160>(st, ma, mb, ma2, mb2, prm, cl);
   if (bn == 128) return bf ? launch_tc<__nv_bfloat16, 128>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 128>(st, ma, mb, ma2, mb2, prm, cl);
   return bf ? launch_tc<__nv_bfloat16, 64>(st, ma, mb, ma2, mb2, prm, cl) : launch_tc<__half, 64>(st, ma, mb, ma2, mb2, prm, cl);
 }

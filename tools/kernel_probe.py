@@ -28,6 +28,10 @@ elif which == "gemm_ff":
     M, K, N = 16384, 1280, 10240
     x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
     fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
+elif which == "gemm640":
+    M, K, N = 65536, 640, 640
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
 elif which == "conv":
     x = torch.randn(16, 1280, 32, 32, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
     w = torch.randn(1280, 1280, 3, 3, device=dev, dtype=bf) * 0.01
