@@ -55,6 +55,23 @@ def measured_peaks() -> tuple[dict, str]:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def usable_cores() -> int:
+    """Host threads this process can really use: affinity mask and cgroup CPU quota, capped at 32
+    (ATen's CPU kernels stop scaling - and oversubscribed boxes collapse - well before 128 threads)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -140,7 +157,7 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     dt_row, sample = cpu_reference_step_seconds(max(1, min(args.warmup, 1)), max(1, args.steps), threads)
     step_s = dt_row * CFG_ROWS
     value = 1.0 / step_s
@@ -188,7 +205,10 @@ def dominant_kernel_roofline(device: torch.device, peaks: dict, peaks_kind: str)
     return {
         "bound": "tensor", "kernel": "tc_gemm_kernel<bf16,256> [16384x1280]x[1280x1280]^T", "achieved": achieved,
         "peak": peak, "peak_source": f"{peaks_kind} bf16_tflops (burst: kernel timed alone)", "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None, "ms_per_launch": ms,
+        "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape, one `ncu --set full` launch
+        # (profiles/r01_ncu_full_gemm_full.txt); algorithmic bytes are 87.2 MB, the output mostly stays in L2
+        "traffic": 47.49e6, "traffic_source": "profiles/r01_ncu_full_gemm_full.txt", "ms_per_launch": ms,
         "algorithmic_flops_per_launch": flops,
     }
 
@@ -332,8 +352,8 @@ def run_gpu_arm(args) -> None:
     }
     cpu = None
     if not args.skip_cpu_baseline:
-        threads = os.cpu_count() or 1
-        log(f'cpu baseline on {threads} threads')
+        threads = usable_cores()
+        log(f'cpu baseline on {threads} threads (os.cpu_count() = {os.cpu_count()})')
         dt_row, sample = cpu_reference_step_seconds(1, 1, threads)
         log('cpu baseline done')
         cpu = {"value": 1.0 / (dt_row * CFG_ROWS), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,

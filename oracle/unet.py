@@ -103,7 +103,8 @@ _SD1_UP = [(False, False), (False, False), (False, True), (True, False), (True, 
 
 def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor) -> Tensor:
     """SD1UNet forward (stable_diffusion_1/unet.py:165-249): 12 down entries each recording a
-    skip, middle block added to the last skip, 12 up entries each consuming one skip."""
+    skip, the middle block (added to the never-written 13th residual slot, i.e. to 0.0), 12 up entries
+    each consuming one skip."""
     dtype = x.dtype
     temb = range_encoder(sd, "TimestepEncoder.RangeEncoder", timestep, dtype)
     skips: list[Tensor] = []

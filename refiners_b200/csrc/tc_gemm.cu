@@ -5,7 +5,7 @@
 // Structure (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer: cp.async.bulk.tensor 4D (A) / 3D (B) -> 128B-swizzled smem ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, SS mode)
-//   warps 2..5  epilogue: tcgen05.ld accumulator -> registers -> bias / LoRA scale / act /
+//   warps 2..9  epilogue: tcgen05.ld accumulator -> registers -> bias / LoRA scale / act /
 //               residual -> 16-byte global stores; overlaps the next tile's main loop through
 //               two TMEM accumulator stages.
 // A is addressed through a 4D tensor map so that the same kernel runs
@@ -29,7 +29,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;   // 64 x 2 bytes = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per 32-lane TMEM group)
 
 struct TcParams {
   int64_t M, N;             // logical output rows / accumulator columns
@@ -268,7 +268,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -378,6 +378,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // =========================================================================== epilogue
     const int lg = warp & 3;             // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;    // warps w and w+4 share a lane group and interleave the column chunks
     const int row = lg * 32 + lane;      // row of the 128-row tile owned by this thread
     T* y = static_cast<T*>(p.y);
     const T* res = static_cast<const T*>(p.residual);
@@ -408,7 +409,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(lg * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int64_t n0 = int64_t(nt) * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t raw[32];

@@ -15,8 +15,6 @@ from __future__ import annotations
 
 import math
 from enum import Enum
-from typing import Any
-
 import torch
 from torch import Tensor, nn
 from torch.nn import functional as F
@@ -356,7 +354,3 @@ class Embedding(nn.Embedding, WeightedModule):
         dtype: DType | None = None,
     ) -> None:
         nn.Embedding.__init__(self, num_embeddings, embedding_dim, device=device, dtype=dtype)
-
-
-def _unused(*_: Any) -> None:  # keeps linters quiet about re-exported names
-    return None
