@@ -81,6 +81,8 @@ int sam_attention_impl(cudaStream_t st, int dtype, const void* qkv, const void* 
   p.o_sb = HW * C; p.o_ss = C;
   p.scale = 1.0f / sqrtf(float(d));
   p.bias_h = bias_h; p.bias_w = bias_w; p.bias_H = Hh; p.bias_W = Ww;
+  // tcgen05 path: head dim 80 runs as two 64-column slabs (TMA zero-fills columns 80..127)
+  if (kernel_mode() != 1 && tc_sdpa_supported(p)) return tc_sdpa(st, p);
   return simt_sdpa(st, p);
 }
 

@@ -27,12 +27,19 @@ namespace {
 
 constexpr int QT = 128;   // queries per tile (UMMA M)
 constexpr int KT = 64;    // keys per tile
-constexpr int HD = 64;    // head dim
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 192;
-constexpr int Q_BYTES = QT * HD * 2, K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2, P_BYTES = QT * KT * 2;
-constexpr int TMEM_COLS = 256;  // S[2]: cols [0, 128), O[2]: cols [128, 256) - double buffered
-constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
+constexpr int P_BYTES = QT * KT * 2;
+constexpr int QSLAB = QT * 64 * 2, KSLAB = KT * 64 * 2;  // one 64-wide (128-byte rows) slab of Q / K / V
+// Head dims are handled in 64-column slabs (HD = 64 or 128): Q, K, V tiles are HD/64 slabs each; S = QK^T
+// accumulates over the slabs, O_j = P V is one N = 64 MMA per slab.  TMEM: S[2] at cols [0,128), O[2] after.
+template <int HD> struct Cfg {
+  static constexpr int NSLAB = HD / 64;
+  static constexpr int Q_BYTES = NSLAB * QSLAB, K_BYTES = NSLAB * KSLAB, V_BYTES = NSLAB * KSLAB;
+  static constexpr int TMEM_COLS = (128 + 2 * HD) <= 256 ? 256 : 512;
+  static constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 + 256;
+  static constexpr int CTAS_PER_SM = HD == 64 ? 2 : 1;
+};
 
 struct AttnParams {
   void* o;
@@ -46,6 +53,11 @@ struct AttnParams {
   float scale2;
   uint32_t idesc_qk, idesc_pv;
   int early_s;  // 1: issue S_{j+1} before P_j V_j (pipelined); 0: strictly after (debug)
+  int d_out;    // output columns per head actually stored (<= HD; SAM: 80 of a zero-padded 128)
+  // optional decomposed relative-position bias (fp32): logit[q, kh * bias_W + kw] += bias_h[b,h,q,kh] + bias_w[b,h,q,kw]
+  const float* bias_h;
+  const float* bias_w;
+  int bias_H, bias_W;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -144,13 +156,15 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-template <typename T, bool DUAL>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+template <typename T, bool DUAL, int HD, bool BIAS>
+__global__ void __launch_bounds__(NUM_THREADS, Cfg<HD>::CTAS_PER_SM)
 tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
                const __grid_constant__ CUtensorMap map_v2, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NSLAB = Cfg<HD>::NSLAB, Q_BYTES = Cfg<HD>::Q_BYTES, K_BYTES = Cfg<HD>::K_BYTES, V_BYTES = Cfg<HD>::V_BYTES;
+  constexpr int TMEM_COLS = Cfg<HD>::TMEM_COLS;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Q_BYTES;
   uint8_t* sV = sK + STAGES * K_BYTES;
@@ -195,7 +209,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;  // buffer b at + 64 * b
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;  // S buffer b at + 64 * b, O buffer b at + HD * b
 
   if (warp == 0) {
     // ================================================================================ TMA
@@ -208,7 +222,8 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int b = int(w / (int64_t(p.n_qt) * p.H));
         mbar_wait(q_empty, qphase ^ 1, 1);
         mbar_arrive_expect_tx(q_full, Q_BYTES);
-        tma_load_4d(sQ, &map_q, q_full, 0, h, qt * QT, b);
+#pragma unroll
+        for (int sl = 0; sl < NSLAB; ++sl) tma_load_4d(sQ + sl * QSLAB, &map_q, q_full, sl * 64, h, qt * QT, b);
         qphase ^= 1;
         for (int set = 0; set < nsets; ++set) {
           const int64_t Sk = set ? p.Sk2 : p.Sk;
@@ -216,8 +231,11 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           for (int j = 0; j < ntiles; ++j) {
             mbar_wait(&kv_empty[stage], phase ^ 1, 2);
             mbar_arrive_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
-            tma_load_4d(sK + stage * K_BYTES, set ? &map_k2 : &map_k, &kv_full[stage], 0, h, j * KT, b);
-            tma_load_4d(sV + stage * V_BYTES, set ? &map_v2 : &map_v, &kv_full[stage], 0, h, j * KT, b);
+#pragma unroll
+            for (int sl = 0; sl < NSLAB; ++sl) {
+              tma_load_4d(sK + stage * K_BYTES + sl * KSLAB, set ? &map_k2 : &map_k, &kv_full[stage], sl * 64, h, j * KT, b);
+              tma_load_4d(sV + stage * V_BYTES + sl * KSLAB, set ? &map_v2 : &map_v, &kv_full[stage], sl * 64, h, j * KT, b);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -232,15 +250,18 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       int st_s = 0, st_pv = 0;      // ring cursors: stage whose K feeds the next S / whose V feeds the next PV
       uint32_t ph_s = 0, qphase = 0;
       uint32_t g = 0;               // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
-      const uint64_t dq = desc_kmajor(smem_u32(sQ));
       auto issue_s = [&](uint32_t gt) {
         const uint32_t b = gt & 1, k_use = gt >> 1;
         mbar_wait(&kv_full[st_s], ph_s, 3);
         mbar_wait(&bar_sfree[b], (k_use & 1) ^ 1, 4);  // previous S in this buffer has been read
         tcgen05_fence_after();
-        const uint64_t dk = desc_kmajor(smem_u32(sK + st_s * K_BYTES));
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s + b * 64, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+        for (int sl = 0; sl < NSLAB; ++sl) {
+          const uint64_t dqs = desc_kmajor(smem_u32(sQ + sl * QSLAB));
+          const uint64_t dk = desc_kmajor(smem_u32(sK + st_s * K_BYTES + sl * KSLAB));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s + b * 64, dqs + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, (sl | k) > 0);
+        }
         umma_commit(&bar_s[b]);
         if (++st_s == STAGES) {
           st_s = 0;
@@ -261,11 +282,14 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             mbar_wait(&bar_p[b], (g >> 1) & 1, 6);  // P_j in smem buffer b; O buffer b has been drained
             tcgen05_fence_after();
             const uint64_t dp = desc_kmajor(smem_u32(sP + b * P_BYTES));
-            const uint64_t dv = desc_mnmajor(smem_u32(sV + st_pv * V_BYTES), V_BYTES);
 #pragma unroll
-            for (int k = 0; k < KT / 16; ++k) {
-              // A: +32 B per 16 keys inside the swizzle atom; B (MN-major): +16 rows * 128 B
-              umma_f16(tmem_o + b * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
+            for (int sl = 0; sl < NSLAB; ++sl) {  // one N = 64 MMA group per 64-column slab of V / O
+              const uint64_t dv = desc_mnmajor(smem_u32(sV + st_pv * V_BYTES + sl * KSLAB), KSLAB);
+#pragma unroll
+              for (int k = 0; k < KT / 16; ++k) {
+                // A: +32 B per 16 keys inside the swizzle atom; B (MN-major): +16 rows * 128 B
+                umma_f16(tmem_o + b * HD + sl * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
+              }
             }
             umma_commit(&kv_empty[st_pv]);  // K_j / V_j slot free once these MMAs retire
             umma_commit(&bar_o[b]);
@@ -321,37 +345,69 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_sfree[buf]);  // the tensor core may overwrite this S buffer
           const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT);
-          if (valid < KT) {
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-              if (i >= valid) s[i] = -INFINITY;
-          }
-          float tmax = s[0];
-#pragma unroll
-          for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
-          const float m_new = fmaxf(m_run, tmax);
-          const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // exp2(-inf) = 0 on the first tile
-          const float mb = m_new * p.scale_log2e;
-          float psum = 0.f;
+          float alpha, psum = 0.f;
           uint32_t packed[KT / 2];
+          if constexpr (BIAS) {
+            // logits in the log2 domain: t = (q.k * scale + bias_h[kh] + bias_w[kw]) * log2(e)
+            const int64_t qrow = (b * p.H + h) * p.Sq + (int64_t(qt) * QT + row < p.Sq ? int64_t(qt) * QT + row : p.Sq - 1);
+            const float* bh = p.bias_h + qrow * p.bias_H;
+            const float* bw = p.bias_w + qrow * p.bias_W;
+            int kh = (j * KT) / p.bias_W, kw = (j * KT) - kh * p.bias_W;
 #pragma unroll
-          for (int i = 0; i < KT; i += 2) {
-            const float p0 = fast_exp2(fmaf(s[i], p.scale_log2e, -mb));
-            const float p1 = fast_exp2(fmaf(s[i + 1], p.scale_log2e, -mb));
-            psum += p0 + p1;
-            packed[i / 2] = pack2<T>(p0, p1);
+            for (int i = 0; i < KT; ++i) {
+              if (i < valid) {
+                s[i] = fmaf(s[i], p.scale_log2e, (__ldg(bh + kh) + __ldg(bw + kw)) * 1.4426950408889634f);
+                if (++kw == p.bias_W) {
+                  kw = 0;
+                  ++kh;
+                }
+              } else {
+                s[i] = -INFINITY;
+              }
+            }
+            float tmax = s[0];
+#pragma unroll
+            for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
+            const float m_new = fmaxf(m_run, tmax);
+            alpha = fast_exp2(m_run - m_new);
+#pragma unroll
+            for (int i = 0; i < KT; i += 2) {
+              const float p0 = fast_exp2(s[i] - m_new), p1 = fast_exp2(s[i + 1] - m_new);
+              psum += p0 + p1;
+              packed[i / 2] = pack2<T>(p0, p1);
+            }
+            m_run = m_new;
+          } else {
+            if (valid < KT) {
+#pragma unroll
+              for (int i = 0; i < KT; ++i)
+                if (i >= valid) s[i] = -INFINITY;
+            }
+            float tmax = s[0];
+#pragma unroll
+            for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
+            const float m_new = fmaxf(m_run, tmax);
+            alpha = fast_exp2((m_run - m_new) * p.scale_log2e);  // exp2(-inf) = 0 on the first tile
+            const float mb = m_new * p.scale_log2e;
+#pragma unroll
+            for (int i = 0; i < KT; i += 2) {
+              const float p0 = fast_exp2(fmaf(s[i], p.scale_log2e, -mb));
+              const float p1 = fast_exp2(fmaf(s[i + 1], p.scale_log2e, -mb));
+              psum += p0 + p1;
+              packed[i / 2] = pack2<T>(p0, p1);
+            }
+            m_run = m_new;
           }
           l_run = l_run * alpha + psum;
-          m_run = m_new;
           if (j > 0) {
             // O_{j-1} = P_{j-1} V_{j-1} landed long ago: fold it in, then rescale to the new maximum
             const uint32_t gp = g - 1, bp = gp & 1;
             mbar_wait(&bar_o[bp], (gp >> 1) & 1, 8);
             tcgen05_fence_after();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < HD / 32; ++half) {
               uint32_t raw[32];
-              tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
+              tmem_ld_32x32(tmem_o + bp * HD + lane_off + half * 32, raw);
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; ++i) acc[half * 32 + i] = (acc[half * 32 + i] + __uint_as_float(raw[i])) * alpha;
@@ -376,9 +432,9 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           tcgen05_fence_after();
           const float wgt = (set ? p.scale2 : 1.f) * (l_run > 0.f ? 1.f / l_run : 0.f);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < HD / 32; ++half) {
             uint32_t raw[32];
-            tmem_ld_32x32(tmem_o + bp * 64 + lane_off + half * 32, raw);
+            tmem_ld_32x32(tmem_o + bp * HD + lane_off + half * 32, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
@@ -392,10 +448,11 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       float* fin = DUAL ? out : acc;
       const int64_t qi = int64_t(qt) * QT + row;
       if (qi < p.Sq) {
-        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * HD;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (p.d_out & 7) == 0) {
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < HD / 8; ++c) {
+            if (c * 8 >= p.d_out) break;
             uint4 v;
             v.x = pack2<T>(fin[c * 8], fin[c * 8 + 1]);
             v.y = pack2<T>(fin[c * 8 + 2], fin[c * 8 + 3]);
@@ -405,7 +462,8 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < HD; ++i) dst[i] = from_f<T>(fin[i]);
+          for (int i = 0; i < HD; ++i)
+            if (i < p.d_out) dst[i] = from_f<T>(fin[i]);
         }
       }
     }
@@ -434,13 +492,13 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// [B, S, H, D] view with strides (sb, ss, D, 1) elements; box = D x 1 x rows x 1
-int make_map(CUtensorMap* map, int dtype, const void* base, int64_t B, int64_t S, int H, int64_t sb, int64_t ss, int rows) {
+// [B, S, H, D] view with strides (sb, ss, D, 1) elements; box = 64 x 1 x rows x 1 (columns >= D are zero filled)
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t B, int64_t S, int H, int64_t sb, int64_t ss, int rows, int D) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) RB200_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
-  const cuuint64_t dims[4] = {cuuint64_t(HD), cuuint64_t(H), cuuint64_t(S), cuuint64_t(B)};
-  const cuuint64_t strides[3] = {cuuint64_t(HD) * 2, cuuint64_t(ss) * 2, cuuint64_t(sb) * 2};
-  const cuuint32_t box[4] = {HD, 1, cuuint32_t(rows), 1};
+  const cuuint64_t dims[4] = {cuuint64_t(D), cuuint64_t(H), cuuint64_t(S), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(D) * 2, cuuint64_t(ss) * 2, cuuint64_t(sb) * 2};
+  const cuuint32_t box[4] = {64, 1, cuuint32_t(rows), 1};  // one 64-column slab per TMA box
   const cuuint32_t es[4] = {1, 1, 1, 1};
   const CUtensorMapDataType dt = dtype == RB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult rc = fn(map, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -453,28 +511,44 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, bool DUAL>
-int launch(cudaStream_t st, const SdpaProblem& s, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-           const CUtensorMap& mk2, const CUtensorMap& mv2, const AttnParams& prm) {
+template <typename T, bool DUAL, int HD, bool BIAS>
+int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
+           const CUtensorMap& mv2, const AttnParams& prm) {
   static bool configured = false;
+  constexpr size_t SMEM = Cfg<HD>::SMEM_BYTES;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
-      RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM);
     configured = true;
   }
-  const int64_t cap = int64_t(sm_count()) * 2;
+  const int64_t cap = int64_t(sm_count()) * Cfg<HD>::CTAS_PER_SM;
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_kernel<T, DUAL><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk, mv, mk2, mv2, prm);
+  tc_sdpa_kernel<T, DUAL, HD, BIAS><<<grid, NUM_THREADS, SMEM, st>>>(mq, mk, mv, mk2, mv2, prm);
   RB200_CHECK_LAUNCH("tc_sdpa");
-  (void)s;
   return 0;
+}
+
+template <typename T>
+int dispatch(cudaStream_t st, const SdpaProblem& p, bool dual, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+             const CUtensorMap& mk2, const CUtensorMap& mv2, const AttnParams& prm) {
+  const bool bias = p.bias_h != nullptr;
+  if (p.D <= 64) {
+    if (bias) RB200_FAIL(-1, "tc_sdpa: bias with head dim 64 is not instantiated");
+    return dual ? launch<T, true, 64, false>(st, mq, mk, mv, mk2, mv2, prm) : launch<T, false, 64, false>(st, mq, mk, mv, mk2, mv2, prm);
+  }
+  if (dual) RB200_FAIL(-1, "tc_sdpa: dual K/V with head dim 128 is not instantiated");
+  return bias ? launch<T, false, 128, true>(st, mq, mk, mv, mk2, mv2, prm) : launch<T, false, 128, false>(st, mq, mk, mv, mk2, mv2, prm);
 }
 
 }  // namespace
 
 bool tc_sdpa_supported(const SdpaProblem& p) {
   if (p.dtype != RB200_BF16 && p.dtype != RB200_FP16) return false;
-  if (p.D != HD || p.causal || p.bias_h != nullptr) return false;
+  // head dims that are not 64 / 128 run zero-padded: the TMA boxes read past D and the out-of-bounds columns are
+  // zero filled, so only D % 8 == 0 (16-byte head offsets) is required.
+  if (p.D < 8 || p.D > 128 || (p.D & 7) != 0 || p.causal) return false;
+  if (p.D <= 64 && p.bias_h != nullptr) return false;
+  if (p.D > 64 && p.k2 != nullptr && p.Sk2 > 0) return false;
   if (p.Sq < 1 || p.Sk < 1 || p.B < 1) return false;
   if (!ok_operand(p.q, p.q_sb, p.q_ss) || !ok_operand(p.k, p.k_sb, p.k_ss) || !ok_operand(p.v, p.v_sb, p.v_ss)) return false;
   if (p.k2 && p.Sk2 > 0 && (!ok_operand(p.k2, p.k2_sb, p.k2_ss) || !ok_operand(p.v2, p.v2_sb, p.v2_ss))) return false;
@@ -484,13 +558,13 @@ bool tc_sdpa_supported(const SdpaProblem& p) {
 
 int tc_sdpa(cudaStream_t st, const SdpaProblem& p) {
   CUtensorMap mq, mk, mv, mk2, mv2;
-  if (int rc = make_map(&mq, p.dtype, p.q, p.B, p.Sq, p.H, p.q_sb, p.q_ss, QT)) return rc;
-  if (int rc = make_map(&mk, p.dtype, p.k, p.B, p.Sk, p.H, p.k_sb, p.k_ss, KT)) return rc;
-  if (int rc = make_map(&mv, p.dtype, p.v, p.B, p.Sk, p.H, p.v_sb, p.v_ss, KT)) return rc;
+  if (int rc = make_map(&mq, p.dtype, p.q, p.B, p.Sq, p.H, p.q_sb, p.q_ss, QT, p.D)) return rc;
+  if (int rc = make_map(&mk, p.dtype, p.k, p.B, p.Sk, p.H, p.k_sb, p.k_ss, KT, p.D)) return rc;
+  if (int rc = make_map(&mv, p.dtype, p.v, p.B, p.Sk, p.H, p.v_sb, p.v_ss, KT, p.D)) return rc;
   const bool dual = p.k2 != nullptr && p.Sk2 > 0;
   if (dual) {
-    if (int rc = make_map(&mk2, p.dtype, p.k2, p.B, p.Sk2, p.H, p.k2_sb, p.k2_ss, KT)) return rc;
-    if (int rc = make_map(&mv2, p.dtype, p.v2, p.B, p.Sk2, p.H, p.v2_sb, p.v2_ss, KT)) return rc;
+    if (int rc = make_map(&mk2, p.dtype, p.k2, p.B, p.Sk2, p.H, p.k2_sb, p.k2_ss, KT, p.D)) return rc;
+    if (int rc = make_map(&mv2, p.dtype, p.v2, p.B, p.Sk2, p.H, p.v2_sb, p.v2_ss, KT, p.D)) return rc;
   } else {
     mk2 = mk;
     mv2 = mv;
@@ -517,9 +591,13 @@ int tc_sdpa(cudaStream_t st, const SdpaProblem& p) {
   prm.early_s = early;
   prm.idesc_qk = common;               // A, B K-major
   prm.idesc_pv = common | (1u << 16);  // B (= V) MN-major
-  if (p.dtype == RB200_BF16)
-    return dual ? launch<__nv_bfloat16, true>(st, p, mq, mk, mv, mk2, mv2, prm) : launch<__nv_bfloat16, false>(st, p, mq, mk, mv, mk2, mv2, prm);
-  return dual ? launch<__half, true>(st, p, mq, mk, mv, mk2, mv2, prm) : launch<__half, false>(st, p, mq, mk, mv, mk2, mv2, prm);
+  prm.d_out = p.D;
+  prm.bias_h = p.bias_h;
+  prm.bias_w = p.bias_w;
+  prm.bias_H = p.bias_H;
+  prm.bias_W = p.bias_W;
+  if (p.dtype == RB200_BF16) return dispatch<__nv_bfloat16>(st, p, dual, mq, mk, mv, mk2, mv2, prm);
+  return dispatch<__half>(st, p, dual, mq, mk, mv, mk2, mv2, prm);
 }
 
 }  // namespace rb200

@@ -254,6 +254,10 @@ SDPA_CASES = [
     (1, 8, 96, 50, 40),      # SD1 head dims
     (1, 8, 40, 40, 80),
     (1, 2, 33, 65, 160),
+    (1, 3, 300, 333, 80),    # two 64-column slabs, zero-filled past 80, ragged tiles
+    (2, 2, 130, 200, 128),
+    (1, 2, 70, 70, 8),
+    (1, 5, 260, 77, 40),
     (2, 3, 128, 4, 64),      # IP-Adapter token count
     (1, 1, 1, 1, 64),
 ]
@@ -279,6 +283,35 @@ def test_sdpa(cuda_device, kernel_mode, dtype, case):
         y = B.sdpa(dev(q), dev(k), dev(v), H)
     # P is rounded to the operand dtype before the PV product in the tensor-core kernel: 4 eps
     assert_close(y, ref, dtype, scale=4.0, what=f"sdpa{case}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("geom", [(2, 14, 14, 4, 80), (1, 9, 5, 2, 80), (1, 16, 16, 3, 64), (1, 20, 20, 2, 32)], ids=str)
+def test_sam_attention(cuda_device, kernel_mode, dtype, geom):
+    """Decomposed relative-position attention (segment_anything/image_encoder.py:87-143 in the
+    reference): logits = q k^T d^-1/2 + rel_h[q, kh] + rel_w[q, kw]."""
+    from refiners_b200 import backend as B
+
+    Bw, Hh, Ww, heads, d = geom
+    C = heads * d
+    qkv = _gen((Bw, Hh, Ww, 3 * C), 90)
+    rel_h, rel_w = _gen((2 * Hh - 1, d), 91), _gen((2 * Ww - 1, d), 92)
+    qkv_r, rh, rw = rounded(qkv, dtype), rounded(rel_h, dtype), rounded(rel_w, dtype)
+    t = qkv_r.reshape(Bw, Hh * Ww, 3, heads, d).permute(2, 0, 3, 1, 4)  # [3, Bw, heads, HW, d]
+    q, k, v = t[0], t[1], t[2]
+    ih = torch.arange(Hh)[:, None] - torch.arange(Hh)[None, :] + Hh - 1
+    iw = torch.arange(Ww)[:, None] - torch.arange(Ww)[None, :] + Ww - 1
+    q5 = q.reshape(Bw, heads, Hh, Ww, d)
+    bias_h = torch.einsum("bnhwc,hkc->bnhwk", q5, rh[ih])
+    bias_w = torch.einsum("bnhwc,wkc->bnhwk", q5, rw[iw])
+    logits = (q * d**-0.5) @ k.transpose(-1, -2)
+    logits = logits.reshape(Bw, heads, Hh, Ww, Hh, Ww) + bias_h[..., :, None] + bias_w[..., None, :]
+    attn = logits.reshape(Bw, heads, Hh * Ww, Hh * Ww).softmax(-1)
+    ref = (attn @ v).transpose(1, 2).reshape(Bw, Hh, Ww, C)
+    dev = lambda x: x.to(cuda_device, dtype)
+    with torch.no_grad():
+        y = B.sam_attention(dev(qkv), dev(rel_h), dev(rel_w), heads)
+    assert_close(y, ref, dtype, scale=4.0, what=f"sam_attention{geom}")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
