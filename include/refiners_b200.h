@@ -138,6 +138,21 @@ int rb200_geglu(void* stream, int dtype, const void* x, void* y, int64_t rows, i
 /* y = a + alpha * b (Residual / Sum of fluxion/layers/chain.py:867-927; Multiply of basics.py:379) */
 int rb200_add(void* stream, int dtype, const void* a, const void* b, void* y, int64_t n, float alpha);
 
+/* ---- SAM ViT data movement ------------------------------------------------------------------
+ * Patch embedding (foundationals/segment_anything/image_encoder.py:9-34 PatchEncoder: Conv2d with
+ * kernel = stride = P) is a GEMM over non-overlapping patches; rb200_patchify lays them out as rows:
+ *   y[(b, ho, wo), (r, s, c)] = x[b, c, ho*P + r, wo*P + s]     y: [B*(H/P)*(W/P), P*P*C]
+ * x is addressed through element strides (sb, sc, sh, sw), so NCHW and channels-last both work.
+ * The matching weight is W[Cout, (r, s, c)]; the product goes through rb200_linear. */
+int rb200_patchify(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t H, int64_t W,
+                   int64_t C, int P, int64_t sb, int64_t sc, int64_t sh, int64_t sw);
+/* Window partition / merge of image_encoder.py:202-237 (WindowPartition: pad + partition; WindowMerge:
+ * merge + crop) on channels-last maps.
+ *   merge == 0: x[B,H,W,C] -> y[B*nH*nW, ws, ws, C], nH = ceil(H/ws), nW = ceil(W/ws), zero padded
+ *   merge != 0: x[B*nH*nW, ws, ws, C] -> y[B,H,W,C] (padding dropped) */
+int rb200_window_partition(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W,
+                           int C, int window, int merge);
+
 /* ---- Scaled dot-product attention -----------------------------------------------------------
  * Replaces fluxion/layers/attentions.py:115-202 (split heads, F.scaled_dot_product_attention,
  * merge heads).  q[B,Sq,H,D], k/v[B,Sk,H,D], o[B,Sq,H,D] addressed through (batch, seq)

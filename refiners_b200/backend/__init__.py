@@ -79,6 +79,8 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_sdpa": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _L, _L, _I] + [_L] * 8 + [_F, _I, _P, _P, _L] + [_L] * 4 + [_F]),
     "rb200_sam_attention_workspace_bytes": (_Z, [_L, _I, _I, _I, _I]),
     "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
+    "rb200_patchify": (_I, [_P, _I, _P, _P, _L, _L, _L, _L, _I, _L, _L, _L, _L]),
+    "rb200_window_partition": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
 }
 
 
@@ -204,6 +206,7 @@ class _PackCache:
 
 
 _conv_cache = _PackCache()
+_patch_cache = _PackCache()
 _geglu_cache = _PackCache()
 _lora_cache = _PackCache()
 _concat_cache = _PackCache()
@@ -451,6 +454,47 @@ def _sam_attention_impl(qkv: Tensor, rel_h: Tensor, rel_w: Tensor, heads: int) -
     return o
 
 
+def _patchify_impl(x: Tensor, patch: int) -> Tensor:
+    lib = load_library()
+    B, C, H, W = x.shape
+    if H % patch or W % patch:
+        raise BackendError(f"patchify: {H}x{W} is not a multiple of the patch size {patch}")
+    y = torch.empty((B * (H // patch) * (W // patch), patch * patch * C), device=x.device, dtype=x.dtype)
+    if y.numel():
+        _check(
+            lib.rb200_patchify(
+                _stream(), _dtype_code(x), x.data_ptr(), y.data_ptr(), B, H, W, C, patch,
+                x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+            )
+        )
+    return y
+
+
+def _window_partition_impl(x: Tensor, window: int) -> Tensor:
+    lib = load_library()
+    B, H, W, C = x.shape
+    xc = x if x.is_contiguous() else x.contiguous()
+    nh, nw = -(-H // window), -(-W // window)
+    y = torch.empty((B * nh * nw, window, window, C), device=x.device, dtype=x.dtype)
+    if y.numel():
+        _check(lib.rb200_window_partition(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), B, H, W, C, window, 0))
+    return y
+
+
+def _window_merge_impl(x: Tensor, window: int, height: int, width: int) -> Tensor:
+    lib = load_library()
+    nh, nw = -(-height // window), -(-width // window)
+    C = x.shape[-1]
+    if x.shape[0] % (nh * nw) or x.shape[1] != window or x.shape[2] != window:
+        raise BackendError(f"window_merge: {tuple(x.shape)} does not tile a {height}x{width} map with window {window}")
+    B = x.shape[0] // (nh * nw)
+    xc = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty((B, height, width, C), device=x.device, dtype=x.dtype)
+    if y.numel():
+        _check(lib.rb200_window_partition(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), B, height, width, C, window, 1))
+    return y
+
+
 # --------------------------------------------------------------- torch custom-op registration
 _torch_lib = torch.library.Library("refiners_b200", "DEF")
 _torch_lib.define(
@@ -470,6 +514,9 @@ _torch_lib.define(
     "sdpa(Tensor q, Tensor k, Tensor v, Tensor? k2, Tensor? v2, int heads, bool causal, float scale2) -> Tensor"
 )
 _torch_lib.define("sam_attention(Tensor qkv, Tensor rel_h, Tensor rel_w, int heads) -> Tensor")
+_torch_lib.define("patchify(Tensor x, int patch) -> Tensor")
+_torch_lib.define("window_partition(Tensor x, int window) -> Tensor")
+_torch_lib.define("window_merge(Tensor x, int window, int height, int width) -> Tensor")
 
 for _name, _fn in (
     ("linear", _linear_impl),
@@ -481,6 +528,9 @@ for _name, _fn in (
     ("add", _add_impl),
     ("sdpa", _sdpa_impl),
     ("sam_attention", _sam_attention_impl),
+    ("patchify", _patchify_impl),
+    ("window_partition", _window_partition_impl),
+    ("window_merge", _window_merge_impl),
 ):
     _torch_lib.impl(_name, _fn, "CUDA")
 
@@ -530,6 +580,24 @@ def _sdpa_fake(q, k, v, k2, v2, heads, causal, scale2):  # type: ignore[no-untyp
 @torch.library.register_fake("refiners_b200::sam_attention")
 def _sam_attention_fake(qkv, rel_h, rel_w, heads):  # type: ignore[no-untyped-def]
     return qkv.new_empty((*qkv.shape[:-1], qkv.shape[-1] // 3))
+
+
+@torch.library.register_fake("refiners_b200::patchify")
+def _patchify_fake(x, patch):  # type: ignore[no-untyped-def]
+    B, C, H, W = x.shape
+    return x.new_empty((B * (H // patch) * (W // patch), patch * patch * C))
+
+
+@torch.library.register_fake("refiners_b200::window_partition")
+def _window_partition_fake(x, window):  # type: ignore[no-untyped-def]
+    B, H, W, C = x.shape
+    return x.new_empty((B * -(-H // window) * -(-W // window), window, window, C))
+
+
+@torch.library.register_fake("refiners_b200::window_merge")
+def _window_merge_fake(x, window, height, width):  # type: ignore[no-untyped-def]
+    n = -(-height // window) * -(-width // window)
+    return x.new_empty((x.shape[0] // n, height, width, x.shape[-1]))
 
 
 _ops = torch.ops.refiners_b200
@@ -650,7 +718,40 @@ def conv2d(
 ) -> Tensor:
     _inference_only(x, weight, bias)
     R, S = weight.shape[2], weight.shape[3]
+    if (
+        R == S == stride
+        and R > 1
+        and padding == 0
+        and chan_bias is None
+        and residual is None
+        and x.shape[2] % R == 0
+        and x.shape[3] % R == 0
+    ):
+        # kernel = stride (ViT patch embedding): a plain GEMM over non-overlapping patches
+        Bn, _, H, W = x.shape
+        y = _ops.linear(_ops.patchify(x, R), patch_gemm_weight(weight), bias, None, None, None, None, epilogue)
+        return y.view(Bn, H // R, W // R, weight.shape[0]).permute(0, 3, 1, 2)
     return _ops.conv2d(x, packed_conv_weight(weight), bias, chan_bias, residual, R, S, stride, padding, epilogue)
+
+
+def patch_gemm_weight(weight: Tensor) -> Tensor:
+    """[Cout, Cin, P, P] -> [Cout, (r, s, c)] matching rb200_patchify's row layout (cached)."""
+    key = _PackCache.key(weight)
+    packed = _patch_cache.get(key, (weight,))
+    if packed is None:
+        packed = weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous()
+        _patch_cache.put(key, (weight,), packed)
+    return packed
+
+
+def window_partition(x: Tensor, window: int) -> Tensor:
+    _inference_only(x)
+    return _ops.window_partition(x, window)
+
+
+def window_merge(x: Tensor, window: int, height: int, width: int) -> Tensor:
+    _inference_only(x)
+    return _ops.window_merge(x, window, height, width)
 
 
 def conv_supported(module: Any) -> bool:

@@ -345,6 +345,68 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
   }
 }
 
+// Non-overlapping P x P patches of an image as GEMM rows: y[(b, ho, wo), (r, s, c)] = x[b, c, ho P + r, wo P + s]
+// (x addressed through element strides, so NCHW and channels-last inputs both work without a layout copy).
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int Ho, int Wo, int C, int P, int64_t sb,
+                                int64_t sc, int64_t sh, int64_t sw) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = int(i % C);
+    int64_t t = i / C;
+    const int s = int(t % P);
+    t /= P;
+    const int r = int(t % P);
+    t /= P;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const int64_t b = t / Ho;
+    y[i] = x[b * sb + c * sc + (int64_t(ho) * P + r) * sh + (int64_t(wo) * P + s) * sw];
+  }
+}
+
+// Window partition (zero padded up to multiples of ws) and its inverse, on channels-last rows of C elements:
+//   partition: y[(b, wh, ww), i, j, :] = x[b, wh ws + i, ww ws + j, :]   (0 outside the H x W map)
+//   merge:     y[b, h, w, :]           = x[(b, h / ws, w / ws), h % ws, w % ws, :]
+template <typename T, bool MERGE>
+__global__ void window_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t B, int H, int W, int C, int ws, int nH, int nW) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V;
+  const int64_t rows = MERGE ? B * H * W : B * nH * nW * ws * ws;
+  const int64_t total = rows * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int v = int(idx % cv);
+    int64_t row = idx / cv;
+    if (MERGE) {
+      const int w = int(row % W);
+      const int h = int((row / W) % H);
+      const int64_t b = row / (int64_t(W) * H);
+      const int64_t src = (((b * nH + h / ws) * nW + w / ws) * ws + h % ws) * ws + w % ws;
+      st16(y + row * C + v * V, ld16(x + src * C + v * V));
+    } else {
+      const int j = int(row % ws);
+      int64_t t = row / ws;
+      const int i = int(t % ws);
+      t /= ws;
+      const int ww = int(t % nW);
+      t /= nW;
+      const int wh = int(t % nH);
+      const int64_t b = t / nH;
+      const int h = wh * ws + i, w = ww * ws + j;
+      Vec16<T> val;
+      if (h < H && w < W) {
+        val = ld16(x + ((b * H + h) * W + w) * C + v * V);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) val.v[e] = from_f<T>(0.f);
+      }
+      st16(y + row * C + v * V, val);
+    }
+  }
+}
+
 template <typename T>
 __global__ void geglu_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int64_t F, int vec_ok) {
   constexpr int V = 16 / sizeof(T);
@@ -521,6 +583,30 @@ int geglu_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows,
     geglu_kernel<T><<<ew_grid(rows * F / V + 1), 256, 0, st>>>((const T*)x, (T*)y, rows, F, vec_ok);
   });
   RB200_CHECK_LAUNCH("geglu");
+  return 0;
+}
+
+int patchify_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, int P, int64_t sb,
+                  int64_t sc, int64_t sh, int64_t sw) {
+  const int64_t Ho = H / P, Wo = W / P, total = B * Ho * Wo * P * P * C;
+  DISPATCH_T(dtype, patchify_kernel<T><<<ew_grid(total), 256, 0, st>>>((const T*)x, (T*)y, total, int(Ho), int(Wo), int(C), P, sb, sc, sh, sw));
+  RB200_CHECK_LAUNCH("patchify");
+  return 0;
+}
+
+int window_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int ws, int merge) {
+  const int nH = (H + ws - 1) / ws, nW = (W + ws - 1) / ws;
+  if (!aligned16(x) || !aligned16(y)) RB200_FAIL(-1, "window: buffers must be 16-byte aligned");
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    if (C % V != 0) RB200_FAIL(-1, "window: C=%d must be a multiple of %d", C, V);
+    const int64_t rows = merge ? B * H * W : B * nH * nW * ws * ws;
+    if (merge)
+      window_kernel<T, true><<<ew_grid(rows * (C / V)), 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, ws, nH, nW);
+    else
+      window_kernel<T, false><<<ew_grid(rows * (C / V)), 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, ws, nH, nW);
+  });
+  RB200_CHECK_LAUNCH("window");
   return 0;
 }
 

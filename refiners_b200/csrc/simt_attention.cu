@@ -71,13 +71,13 @@ __global__ void __launch_bounds__(NT) simt_sdpa_kernel(const SdpaProblem p) {
         for (int jj = 0; jj < 8; ++jj) s[jj] = fmaf(qv, Ks[(part * 8 + jj) * (D + 1) + d], s[jj]);
       }
       if (p.bias_h != nullptr && set == 0 && q0 + r < p.Sq) {
-        const int64_t qrow = (b * p.H + h) * p.Sq + (q0 + r);
-        const float* bh = p.bias_h + qrow * p.bias_H;
-        const float* bw = p.bias_w + qrow * p.bias_W;
+        // tables are [b, head, k, q] (q fastest)
+        const float* bh = p.bias_h + (b * p.H + h) * p.bias_H * p.Sq + (q0 + r);
+        const float* bw = p.bias_w + (b * p.H + h) * p.bias_W * p.Sq + (q0 + r);
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int64_t kj = kt + part * 8 + jj;
-          if (kj < Sk) s[jj] = (s[jj] + bh[kj / p.bias_W]) + bw[kj % p.bias_W];  // vertical term first, as in the reference
+          if (kj < Sk) s[jj] = (s[jj] + bh[(kj / p.bias_W) * p.Sq]) + bw[(kj % p.bias_W) * p.Sq];  // vertical term first, as in the reference
         }
       }
       float tmax = -INFINITY;

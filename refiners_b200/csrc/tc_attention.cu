@@ -54,7 +54,7 @@ struct AttnParams {
   uint32_t idesc_qk, idesc_pv;
   int early_s;  // 1: issue S_{j+1} before P_j V_j (pipelined); 0: strictly after (debug)
   int d_out;    // output columns per head actually stored (<= HD; SAM: 80 of a zero-padded 128)
-  // optional decomposed relative-position bias (fp32): logit[q, kh * bias_W + kw] += bias_h[b,h,q,kh] + bias_w[b,h,q,kw]
+  // optional decomposed relative-position bias (fp32): logit[q, kh * bias_W + kw] += bias_h[b,h,kh,q] + bias_w[b,h,kw,q]
   const float* bias_h;
   const float* bias_w;
   int bias_H, bias_W;
@@ -348,18 +348,22 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           float alpha, psum = 0.f;
           uint32_t packed[KT / 2];
           if constexpr (BIAS) {
-            // logits in the log2 domain: t = (q.k * scale + bias_h[kh] + bias_w[kw]) * log2(e)
-            const int64_t qrow = (b * p.H + h) * p.Sq + (int64_t(qt) * QT + row < p.Sq ? int64_t(qt) * QT + row : p.Sq - 1);
-            const float* bh = p.bias_h + qrow * p.bias_H;
-            const float* bw = p.bias_w + qrow * p.bias_W;
+            // logits in the log2 domain: t = (q.k * scale + bias_h[kh] + bias_w[kw]) * log2(e).  The tables are
+            // [b, head, k, q] with q fastest, so the 32 rows of a warp read one 128-byte line per (k) - coalesced.
+            constexpr float L2E = 1.4426950408889634f;
+            const int64_t qcl = int64_t(qt) * QT + row < p.Sq ? int64_t(qt) * QT + row : p.Sq - 1;
+            const float* bh = p.bias_h + (b * p.H + h) * int64_t(p.bias_H) * p.Sq + qcl;
+            const float* bw = p.bias_w + (b * p.H + h) * int64_t(p.bias_W) * p.Sq + qcl;
             int kh = (j * KT) / p.bias_W, kw = (j * KT) - kh * p.bias_W;
+            float bhv = __ldg(bh + int64_t(kh) * p.Sq) * L2E;
 #pragma unroll
             for (int i = 0; i < KT; ++i) {
               if (i < valid) {
-                s[i] = fmaf(s[i], p.scale_log2e, (__ldg(bh + kh) + __ldg(bw + kw)) * 1.4426950408889634f);
+                s[i] = fmaf(s[i], p.scale_log2e, fmaf(__ldg(bw + int64_t(kw) * p.Sq), L2E, bhv));
                 if (++kw == p.bias_W) {
                   kw = 0;
                   ++kh;
+                  if (kh < p.bias_H) bhv = __ldg(bh + int64_t(kh) * p.Sq) * L2E;
                 }
               } else {
                 s[i] = -INFINITY;

@@ -7,6 +7,7 @@ change (``Chain._regenerate_keys`` drops it).  A plan is a list of steps:
   ("call", name, layer)                    run the child as the reference would
   ("gn_silu", name, gn, silu)              GroupNorm -> SiLU            => one rb200_group_norm launch
   ("linear_geglu", name, linear, glu)      Linear -> GLU(GeLU)          => GEMM with GEGLU epilogue
+  ("linear_act", name, linear, act, epi)   Linear -> GeLU (erf) | SiLU  => GEMM with activation epilogue
 
 and two tail fusions used by the containers that add a skip connection:
 
@@ -52,6 +53,11 @@ def build_plan(chain: Any) -> list[tuple[Any, ...]]:
         ):
             plan.append(("linear_geglu", name, layer, nxt))
             i += 2
+        elif type(layer) is Linear and (
+            type(nxt) is SiLU or (type(nxt) is GeLU and nxt.approximation is GeLUApproximation.NONE)
+        ):
+            plan.append(("linear_act", name, layer, nxt, B.EPI_SILU if type(nxt) is SiLU else B.EPI_GELU))
+            i += 2
         else:
             plan.append(("call", name, layer))
             i += 1
@@ -80,6 +86,9 @@ def run_steps(chain: Any, steps: list[tuple[Any, ...]], args: tuple[Any, ...]) -
         ):
             lin = step[2]
             result = chain._call_fused(step[1], lambda x, lin=lin: B.linear_geglu(x, lin.weight, lin.bias), *args)
+        elif kind == "linear_act" and fuse and _cuda_tensor(args) and not _hooked(step[2], step[3]):
+            lin, epi = step[2], step[4]
+            result = chain._call_fused(step[1], lambda x, lin=lin, epi=epi: B.linear(x, lin.weight, lin.bias, epilogue=epi), *args)
         elif kind == "call":
             result = chain._call_layer(step[2], step[1], *args)
         else:  # unfused pair

@@ -178,10 +178,12 @@ class WindowPartition(fl.ContextModule):
         ctx = self.use_context("window_partition")
         ws = ctx["window_size"]
         ph, pw = (ws - height % ws) % ws, (ws - width % ws) % ws
-        if ph or pw:
-            x = pad(x, (0, 0, 0, pw, 0, ph))
         hp, wp = height + ph, width + pw
         ctx.update({"original_height": height, "original_width": width, "padded_height": hp, "padded_width": wp})
+        if x.is_cuda and channels % (16 // x.element_size()) == 0:
+            return B.window_partition(x, ws)  # pad + partition in one launch
+        if ph or pw:
+            x = pad(x, (0, 0, 0, pw, 0, ph))
         x = x.view(batch, hp // ws, ws, wp // ws, ws, channels)
         return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws, ws, channels)
 
@@ -195,6 +197,8 @@ class WindowMerge(fl.ContextModule):
         ws = ctx["window_size"]
         hp, wp = ctx["padded_height"], ctx["padded_width"]
         height, width = ctx["original_height"], ctx["original_width"]
+        if x.is_cuda and x.shape[-1] % (16 // x.element_size()) == 0:
+            return B.window_merge(x, ws, height, width)  # merge + crop in one launch
         batch = x.shape[0] // (hp * wp // ws // ws)
         x = x.view(batch, hp // ws, wp // ws, ws, ws, -1).permute(0, 1, 3, 2, 4, 5).contiguous().view(batch, hp, wp, -1)
         if hp > height or wp > width:

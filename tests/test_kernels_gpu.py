@@ -132,7 +132,9 @@ CONV_CASES = [
     (2, 320, 16, 16, 4, 3, 1, 1),     # UNet output conv: Cout = 4
     (4, 128, 8, 8, 128, 3, 1, 1),     # 8x8 map: one tile spans two images
     (1, 96, 24, 40, 80, 3, 1, 1),     # odd geometry
-    (1, 8, 64, 64, 32, 16, 16, 0),    # patch embedding style (kernel = stride = 16)
+    (1, 8, 64, 64, 32, 16, 16, 0),    # patch embedding style (kernel = stride = 16): patchify + GEMM
+    (2, 3, 64, 96, 160, 16, 16, 0),   # SAM PatchEncoder: Cin = 3
+    (1, 5, 12, 12, 7, 4, 4, 0),       # odd channel counts -> CUDA-core GEMM
 ]
 
 
@@ -150,6 +152,25 @@ def test_conv2d(cuda_device, kernel_mode, dtype, case):
         y = B.conv2d(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype), stride, pad)
     assert y.shape == ref.shape
     assert_close(y, ref, dtype, what=f"conv{case}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("geom", [(2, 64, 64, 32, 14), (1, 9, 20, 16, 7), (3, 8, 8, 8, 8), (1, 5, 3, 8, 4)], ids=str)
+def test_window_partition_merge(cuda_device, dtype, geom):
+    """WindowPartition / WindowMerge of the SAM encoder (image_encoder.py:202-237 in the reference)."""
+    from refiners_b200 import backend as B
+
+    Bn, H, W, C, ws = geom
+    x = _gen((Bn, H, W, C), 48).to(dtype)
+    ph, pw = (ws - H % ws) % ws, (ws - W % ws) % ws
+    xp = F.pad(x, (0, 0, 0, pw, 0, ph))
+    hp, wp = H + ph, W + pw
+    ref = xp.view(Bn, hp // ws, ws, wp // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, C)
+    with torch.no_grad():
+        y = B.window_partition(x.to(cuda_device), ws)
+        back = B.window_merge(y, ws, H, W)
+    assert torch.equal(y.cpu(), ref)
+    assert torch.equal(back.cpu(), x)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
