@@ -71,13 +71,14 @@ __global__ void __launch_bounds__(NT) simt_sdpa_kernel(const SdpaProblem p) {
         for (int jj = 0; jj < 8; ++jj) s[jj] = fmaf(qv, Ks[(part * 8 + jj) * (D + 1) + d], s[jj]);
       }
       if (p.bias_h != nullptr && set == 0 && q0 + r < p.Sq) {
-        // tables are [b, head, k, q] (q fastest)
-        const float* bh = p.bias_h + (b * p.H + h) * p.bias_H * p.Sq + (q0 + r);
-        const float* bw = p.bias_w + (b * p.H + h) * p.bias_W * p.Sq + (q0 + r);
+        // one block of (bias_H + bias_W) x 128 floats per (b, head, 128-query tile): [k][q % 128]
+        const int64_t qq = q0 + r, nqt = (p.Sq + 127) / 128;
+        const float* bh = p.bias_h + (((b * p.H + h) * nqt + qq / 128) * (p.bias_H + p.bias_W)) * 128 + qq % 128;
+        const float* bw = bh + p.bias_H * 128;
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int64_t kj = kt + part * 8 + jj;
-          if (kj < Sk) s[jj] = (s[jj] + bh[(kj / p.bias_W) * p.Sq]) + bw[(kj % p.bias_W) * p.Sq];  // vertical term first, as in the reference
+          if (kj < Sk) s[jj] = (s[jj] + bh[(kj / p.bias_W) * 128]) + bw[(kj % p.bias_W) * 128];  // vertical term first, as in the reference
         }
       }
       float tmax = -INFINITY;

@@ -30,6 +30,7 @@ constexpr int KT = 64;    // keys per tile
 constexpr int STAGES = 3;
 constexpr int NUM_THREADS = 192;
 constexpr int P_BYTES = QT * KT * 2;
+constexpr int MAX_BIAS_BYTES = 64 * 1024;  // staged bias block: (bias_H + bias_W) * 128 floats
 constexpr int QSLAB = QT * 64 * 2, KSLAB = KT * 64 * 2;  // one 64-wide (128-byte rows) slab of Q / K / V
 // Head dims are handled in 64-column slabs (HD = 64 or 128): Q, K, V tiles are HD/64 slabs each; S = QK^T
 // accumulates over the slabs, O_j = P V is one N = 64 MMA per slab.  TMEM: S[2] at cols [0,128), O[2] after.
@@ -54,10 +55,12 @@ struct AttnParams {
   uint32_t idesc_qk, idesc_pv;
   int early_s;  // 1: issue S_{j+1} before P_j V_j (pipelined); 0: strictly after (debug)
   int d_out;    // output columns per head actually stored (<= HD; SAM: 80 of a zero-padded 128)
-  // optional decomposed relative-position bias (fp32): logit[q, kh * bias_W + kw] += bias_h[b,h,kh,q] + bias_w[b,h,kw,q]
-  const float* bias_h;
-  const float* bias_w;
+  // optional decomposed relative-position bias (fp32), one block of (bias_H + bias_W) x 128 floats per (b, h, q tile):
+  //   logit[q, kh * bias_W + kw] += bias[b, h, q / 128, kh, q % 128] + bias[b, h, q / 128, bias_H + kw, q % 128]
+  // The block of a work item is staged in shared memory with one bulk copy.
+  const float* bias;
   int bias_H, bias_W;
+  uint32_t bias_bytes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -96,6 +99,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -179,6 +187,9 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* bar_p = q_full + 6;          // [2] P tile written to smem buffer b (previous O consumed)
   uint64_t* bar_o = q_full + 8;          // [2] O_j ready in TMEM buffer b (P buffer and V slot consumed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 10);
+  uint64_t* bias_full = q_full + 12;     // bias block of this work item landed in sBias
+  uint64_t* bias_empty = q_full + 13;    // the four softmax warps are done with it
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [(bias_H + bias_W)][128], BIAS only
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsets = DUAL ? 2 : 1;
@@ -193,6 +204,8 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
+    mbar_init(bias_full, 1);
+    mbar_init(bias_empty, 4);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_s[b], 1);
       mbar_init(&bar_sfree[b], 4);
@@ -224,6 +237,11 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_arrive_expect_tx(q_full, Q_BYTES);
 #pragma unroll
         for (int sl = 0; sl < NSLAB; ++sl) tma_load_4d(sQ + sl * QSLAB, &map_q, q_full, sl * 64, h, qt * QT, b);
+        if constexpr (BIAS) {
+          mbar_wait(bias_empty, qphase ^ 1, 8);
+          mbar_arrive_expect_tx(bias_full, p.bias_bytes);
+          bulk_load(sBias, reinterpret_cast<const uint8_t*>(p.bias) + w * int64_t(p.bias_bytes), p.bias_bytes, bias_full);
+        }
         qphase ^= 1;
         for (int set = 0; set < nsets; ++set) {
           const int64_t Sk = set ? p.Sk2 : p.Sk;
@@ -306,6 +324,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int row = lg * 32 + lane;
     const uint32_t lane_off = uint32_t(lg * 32) << 16;
     uint32_t g = 0;  // global tile counter, in step with the MMA warp
+    uint32_t bias_phase = 0;
     uint8_t* prow = sP + row * 128;
     const int sw = row & 7;
     T* obase = static_cast<T*>(p.o);
@@ -319,6 +338,10 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         for (int i = 0; i < HD; ++i) out[i] = 0.f;
       }
       float acc[HD];
+      if constexpr (BIAS) {
+        mbar_wait(bias_full, bias_phase, 9);
+        bias_phase ^= 1;
+      }
       for (int set = 0; set < nsets; ++set) {
         const int64_t Sk = set ? p.Sk2 : p.Sk;
         const int ntiles = int((Sk + KT - 1) / KT);
@@ -348,26 +371,35 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           float alpha, psum = 0.f;
           uint32_t packed[KT / 2];
           if constexpr (BIAS) {
-            // logits in the log2 domain: t = (q.k * scale + bias_h[kh] + bias_w[kw]) * log2(e).  The tables are
-            // [b, head, k, q] with q fastest, so the 32 rows of a warp read one 128-byte line per (k) - coalesced.
+            // logits in the log2 domain: t = (q.k * scale + bias_h[kh] + bias_w[kw]) * log2(e); this row's entries
+            // sit at sBias[k * 128 + row] (conflict free across the lanes of a warp).
             constexpr float L2E = 1.4426950408889634f;
-            const int64_t qcl = int64_t(qt) * QT + row < p.Sq ? int64_t(qt) * QT + row : p.Sq - 1;
-            const float* bh = p.bias_h + (b * p.H + h) * int64_t(p.bias_H) * p.Sq + qcl;
-            const float* bw = p.bias_w + (b * p.H + h) * int64_t(p.bias_W) * p.Sq + qcl;
-            int kh = (j * KT) / p.bias_W, kw = (j * KT) - kh * p.bias_W;
-            float bhv = __ldg(bh + int64_t(kh) * p.Sq) * L2E;
+            const float* sbh = sBias + row;
+            const float* sbw = sbh + p.bias_H * 128;
+            if (p.bias_W == KT) {  // every key tile is one full row of the map: kh = j, kw = i
+              const float bhv = sbh[j * 128] * L2E;
 #pragma unroll
-            for (int i = 0; i < KT; ++i) {
-              if (i < valid) {
-                s[i] = fmaf(s[i], p.scale_log2e, fmaf(__ldg(bw + int64_t(kw) * p.Sq), L2E, bhv));
-                if (++kw == p.bias_W) {
-                  kw = 0;
-                  ++kh;
-                  if (kh < p.bias_H) bhv = __ldg(bh + int64_t(kh) * p.Sq) * L2E;
+              for (int i = 0; i < KT; ++i) s[i] = i < valid ? fmaf(s[i], p.scale_log2e, fmaf(sbw[i * 128], L2E, bhv)) : -INFINITY;
+            } else {
+              int kh = (j * KT) / p.bias_W, kw = (j * KT) - kh * p.bias_W;
+              float bhv = sbh[kh * 128] * L2E;
+#pragma unroll
+              for (int i = 0; i < KT; ++i) {
+                if (i < valid) {
+                  s[i] = fmaf(s[i], p.scale_log2e, fmaf(sbw[kw * 128], L2E, bhv));
+                  if (++kw == p.bias_W) {
+                    kw = 0;
+                    ++kh;
+                    if (kh < p.bias_H) bhv = sbh[kh * 128] * L2E;
+                  }
+                } else {
+                  s[i] = -INFINITY;
                 }
-              } else {
-                s[i] = -INFINITY;
               }
+            }
+            if (j == ntiles - 1) {  // last read of this work item's bias block
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bias_empty);
             }
             float tmax = s[0];
 #pragma unroll
@@ -519,10 +551,11 @@ template <typename T, bool DUAL, int HD, bool BIAS>
 int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
            const CUtensorMap& mv2, const AttnParams& prm) {
   static bool configured = false;
-  constexpr size_t SMEM = Cfg<HD>::SMEM_BYTES;
+  constexpr size_t SMEM_MAX = Cfg<HD>::SMEM_BYTES + (BIAS ? MAX_BIAS_BYTES : 0);
+  const size_t SMEM = Cfg<HD>::SMEM_BYTES + (BIAS ? prm.bias_bytes : 0);
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
-      RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM);
+    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_MAX)) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM_MAX);
     configured = true;
   }
   const int64_t cap = int64_t(sm_count()) * Cfg<HD>::CTAS_PER_SM;
@@ -552,6 +585,7 @@ bool tc_sdpa_supported(const SdpaProblem& p) {
   // zero filled, so only D % 8 == 0 (16-byte head offsets) is required.
   if (p.D < 8 || p.D > 128 || (p.D & 7) != 0 || p.causal) return false;
   if (p.D <= 64 && p.bias_h != nullptr) return false;
+  if (p.bias_h != nullptr && (p.bias_H + p.bias_W) * 512 > MAX_BIAS_BYTES) return false;
   if (p.D > 64 && p.k2 != nullptr && p.Sk2 > 0) return false;
   if (p.Sq < 1 || p.Sk < 1 || p.B < 1) return false;
   if (!ok_operand(p.q, p.q_sb, p.q_ss) || !ok_operand(p.k, p.k_sb, p.k_ss) || !ok_operand(p.v, p.v_sb, p.v_ss)) return false;
@@ -596,10 +630,10 @@ int tc_sdpa(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_qk = common;               // A, B K-major
   prm.idesc_pv = common | (1u << 16);  // B (= V) MN-major
   prm.d_out = p.D;
-  prm.bias_h = p.bias_h;
-  prm.bias_w = p.bias_w;
+  prm.bias = p.bias_h;
   prm.bias_H = p.bias_H;
   prm.bias_W = p.bias_W;
+  prm.bias_bytes = uint32_t(p.bias_H + p.bias_W) * 512u;
   if (p.dtype == RB200_BF16) return dispatch<__nv_bfloat16>(st, p, dual, mq, mk, mv, mk2, mv2, prm);
   return dispatch<__half>(st, p, dual, mq, mk, mv, mk2, mv2, prm);
 }

@@ -451,7 +451,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int64_t no = n0 >> 1;
           float o[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf(v[16 + j]);
+          for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_fast(v[16 + j]);
           T* dst = y + m_lin * p.ldy + no;
           if (res) {
             const T* rs = res + m_lin * p.ldr + no;
@@ -477,7 +477,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (p.epilogue != RB200_EPI_NONE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_epilogue(v[j], p.epilogue);
+          for (int j = 0; j < 32; ++j) v[j] = apply_epilogue_fast(v[j], p.epilogue);
         }
         T* dst = y + m_lin * p.ldy + n0;
         if (res) {
