@@ -113,6 +113,29 @@ __device__ __forceinline__ void tma_load_3d_mcast(void* dst, const CUtensorMap* 
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// CTA-pair (cta_group::2) loads: data lands in THIS CTA's smem, the transaction bytes are credited to the mbarrier at
+// `bar_cluster_addr` - a shared::cluster address, here always the leader CTA's full barrier (see mapa_rank0)
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// shared::cluster address of the variable at the same offset in CTA 0 of the cluster
+__device__ __forceinline__ uint32_t mapa_rank0(const void* local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(local)));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -138,6 +161,16 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
+// CTA-pair flavours: one warp of EACH CTA of the pair executes them
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
 
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -147,6 +180,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// CTA-pair MMA, issued by the leader only: D[256 x N] = A[256 x 16] B[N x 16]^T.  Rows 0..127 of A / D live in the
+// leader's smem / TMEM, rows 128..255 in the peer's (same offsets); B rows [0, N/2) in the leader's smem, [N/2, N) in the peer's.
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -211,15 +257,37 @@ __device__ __forceinline__ void add8(float* v, const T* p) {
   }
 }
 
+template <typename T>
+__device__ __forceinline__ void add8v(float* v, const uint4 u) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = unpack2<T>(w[i]);
+    v[2 * i] += f.x;
+    v[2 * i + 1] += f.y;
+  }
+}
+
 template <int BN> struct TileCfg;
 template <> struct TileCfg<256> { static constexpr int STAGES = 4; };
 template <> struct TileCfg<160> { static constexpr int STAGES = 5; };  // 320, 640, 1280 = k * 160 exactly
 template <> struct TileCfg<128> { static constexpr int STAGES = 6; };
 template <> struct TileCfg<64> { static constexpr int STAGES = 8; };
 
-template <int BN>
+// CTA-pair mode keeps only half of the B tile per CTA: smaller stages, deeper pipelines
+template <int BN> struct PairCfg;
+template <> struct PairCfg<256> { static constexpr int STAGES = 6; };
+template <> struct PairCfg<160> { static constexpr int STAGES = 8; };
+template <> struct PairCfg<128> { static constexpr int STAGES = 8; };
+template <> struct PairCfg<64> { static constexpr int STAGES = 8; };
+
+// MODE 1: one CTA per 128 x BN tile.  MODE 2: two CTAs per cluster on vertically adjacent tiles, B tile multicast.
+// MODE 3: CTA pair, one 256 x BN tile per pair with cta_group::2 MMAs (B split between the two CTAs' smem).
+template <int BN, int MODE>
+constexpr int stages_of() { return MODE == 3 ? PairCfg<BN>::STAGES : TileCfg<BN>::STAGES; }
+template <int BN, int MODE>
 constexpr size_t smem_bytes() {
-  return size_t(TileCfg<BN>::STAGES) * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
+  return size_t(stages_of<BN, MODE>()) * (BM * BK * 2 + (MODE == 3 ? BN / 2 : BN) * BK * 2) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
 // --------------------------------------------------------------------------------- the kernel
@@ -227,13 +295,20 @@ constexpr size_t smem_bytes() {
 // (same N range): each loads its own A tile and HALF of the shared B tile, multicast into both
 // CTAs' smem - L2->SM traffic per CTA-iteration drops from A+B to A+B/2 (48 KB -> 32 KB at
 // BN = 256), which matters because the kernel is L2-bandwidth- rather than MMA-bound.
-template <typename T, int BN, int CL>
+//
+// MODE 3 (PAIR) replaces the multicast by a cta_group::2 MMA: the pair computes ONE 256 x BN tile, each CTA stages its
+// own 128 rows of A and HALF of B (no duplication), only the leader (rank 0) issues MMAs, and every TMA of either CTA
+// credits the leader's full barrier.  Per-CTA smem operand reads per flop drop from (128 + BN) to (128 + BN / 2) rows,
+// which is what lets 160-wide tiles (8 x 160 = 1280: no wave-quantisation loss on the N = 1280 layers) run at full rate.
+template <typename T, int BN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
                const TcParams p) {
-  constexpr int STAGES = TileCfg<BN>::STAGES;
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int CL = MODE == 1 ? 1 : 2;
+  constexpr bool PAIR = MODE == 3;
+  constexpr int STAGES = stages_of<BN, MODE>();
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
@@ -264,15 +339,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);  // every CTA that reads this slot (it is written by all of them)
+      // MODE 2: every CTA that reads this slot commits (it is written by all of them); PAIR: the leader's one commit
+      mbar_init(&empty_bar[s], PAIR ? 1 : CL);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], PAIR ? 16 : 8);  // PAIR: the epilogue warps of both CTAs release the leader's MMA warp
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tcgen05_fence_before();
   __syncthreads();
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers exist before anyone signals them
@@ -304,9 +383,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int tap = 0, kb = 0;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           void* da = smem_a + size_t(stage) * A_BYTES;
           void* db = smem_b + size_t(stage) * B_BYTES;
+          if constexpr (PAIR) {
+            // the leader's barrier collects both CTAs' bytes; the peer only issues its loads
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_BYTES + B_BYTES));
+            const uint32_t lead_bar = mapa_rank0(&full_bar[stage]);
+            if (it < p.k_iters1) {
+              const int r = tap / p.kw, s = tap - r * p.kw;
+              tma_load_4d_pair(da, &map_a, lead_bar, kb * BK, a1 + s, a2 + r, a3);
+              tma_load_3d_pair(db, &map_b, lead_bar, kb * BK, n0 + cta_rank * (BN / 2), tap);
+              if (++kb == p.kblocks) {
+                kb = 0;
+                ++tap;
+              }
+            } else {
+              const int kb2 = it - p.k_iters1;
+              tma_load_4d_pair(da, &map_a2, lead_bar, kb2 * BK, mt * BM, 0, 0);
+              tma_load_3d_pair(db, &map_b2, lead_bar, kb2 * BK, n0 + cta_rank * (BN / 2), 0);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           if (it < p.k_iters1) {
             const int r = tap / p.kw, s = tap - r * p.kw;
             tma_load_4d(da, &map_a, &full_bar[stage], kb * BK, a1 + s, a2 + r, a3);
@@ -340,7 +442,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ========================================================================= MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {  // PAIR: the leader drives both tensor cores
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -358,17 +460,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing 16 elements (32 bytes) along K inside the swizzle atom: +2 in the
             // 16-byte-granular start-address field
-            umma_f16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_f16_pair(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_f16(tmem_d, da + uint64_t(k * 2), db + uint64_t(k * 2), p.idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in every CTA that writes into it) when these MMAs retire
-          if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], uint16_t((1u << CL) - 1));
+          if constexpr (PAIR) umma_commit_pair_mcast(&empty_bar[stage], uint16_t(3));
+          else if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], uint16_t((1u << CL) - 1));
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (PAIR: of both CTAs, each reads its own 128 rows from its own TMEM)
+        if constexpr (PAIR) umma_commit_pair_mcast(&tfull_bar[acc], uint16_t(3));
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -405,11 +511,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         m_lin = int64_t(mt) * BM + row;
         valid = m_lin < p.M;
       }
+      // The residual rows of this tile are fetched BEFORE waiting for the accumulator, while the tensor core is
+      // still working on it: the epilogue then never sits on a dependent global-load latency per column chunk.
+      constexpr int MAXC = (BN / 32 + 1) / 2;
+      uint4 rpre[MAXC][4];
+      const bool rfast = res != nullptr && !geglu && valid && (int64_t(nt) * BN + BN <= p.N) &&
+                         ((reinterpret_cast<uintptr_t>(res + m_lin * p.ldr + int64_t(nt) * BN) & 15) == 0);
+      if (rfast) {
+        const uint4* rs = reinterpret_cast<const uint4*>(res + m_lin * p.ldr + int64_t(nt) * BN);
+#pragma unroll
+        for (int cc = 0; cc < MAXC; ++cc) {
+          const int c = half + 2 * cc;
+          if (c < BN / 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rpre[cc][q] = __ldg(rs + c * 4 + q);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(lg * 32) << 16);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+#pragma unroll
+      for (int cc = 0; cc < MAXC; ++cc) {
+        const int c = half + 2 * cc;
+        if (c >= BN / 32) break;
         const int64_t n0 = int64_t(nt) * BN + c * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t raw[32];
@@ -480,7 +605,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = apply_epilogue_fast(v[j], p.epilogue);
         }
         T* dst = y + m_lin * p.ldy + n0;
-        if (res) {
+        if (rfast) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) add8v<T>(v + 8 * q, rpre[cc][q]);
+        } else if (res) {
           const T* rs = res + m_lin * p.ldr + n0;
           if (full && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
 #pragma unroll
@@ -510,7 +638,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // all TMEM reads of this warp are complete (wait::ld above): release the accumulator
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_rank0(&tempty_bar[acc]));  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -523,7 +654,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if constexpr (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still write/signal here
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -581,25 +713,28 @@ bool pick_conv_tile(int64_t B, int64_t Ho, int64_t Wo, int* TW, int* TH, int* TB
 template <typename T, int BN, int CL>
 int launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mb2,
                  TcParams& prm) {
+  constexpr int MODE = CL;  // template argument: 1 single CTA, 2 multicast pair, 3 cta_group::2 pair
+  constexpr int CLUSTER = MODE == 1 ? 1 : 2;
   static bool configured = false;
-  constexpr size_t SMEM = smem_bytes<BN>();
+  constexpr size_t SMEM = smem_bytes<BN, MODE>();
+  if (MODE == 3) prm.idesc = (prm.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);  // UMMA M = 256 across the pair
   if (!configured) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<T, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
       RB200_FAIL(-2, "tc_gemm: cannot reserve %zu bytes of shared memory", SMEM);
     configured = true;
   }
-  const int64_t groups = int64_t((prm.tiles_m + CL - 1) / CL) * prm.tiles_n;
+  const int64_t groups = int64_t((prm.tiles_m + CLUSTER - 1) / CLUSTER) * prm.tiles_n;
   if (groups > (int64_t(1) << 30)) RB200_FAIL(-1, "tc_gemm: too many tiles");
-  const int64_t max_clusters = sm_count() / CL;
+  const int64_t max_clusters = sm_count() / CLUSTER;
   const int clusters = int(groups < max_clusters ? groups : max_clusters);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(unsigned(clusters * CL));
+  cfg.gridDim = dim3(unsigned(clusters * CLUSTER));
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = CLUSTER;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -612,8 +747,9 @@ int launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, 
 
 int cluster_mode() {
   static const int mode = [] {
-    const char* e = getenv("RB200_GEMM_CLUSTER");  // 1 disables the multicast pairing (A/B runs)
-    return e ? atoi(e) : 2;
+    // 1: one CTA per tile; 2: CTA pairs with B multicast; 3 (default): CTA pairs with cta_group::2 MMAs
+    const char* e = getenv("RB200_GEMM_CLUSTER");
+    return e ? atoi(e) : 3;
   }();
   return mode;
 }
@@ -622,7 +758,7 @@ template <typename T, int BN>
 int launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& ma2, const CUtensorMap& mb2,
               TcParams& prm, int cl) {
   prm.tiles_n = int(ceil_div(prm.N, BN));
-  if (cl == 2) return launch_tc_cl<T, BN, 2>(st, ma, mb, ma2, mb2, prm);
+  if (cl == 2) return cluster_mode() >= 3 ? launch_tc_cl<T, BN, 3>(st, ma, mb, ma2, mb2, prm) : launch_tc_cl<T, BN, 2>(st, ma, mb, ma2, mb2, prm);
   return launch_tc_cl<T, BN, 1>(st, ma, mb, ma2, mb2, prm);
 }
 
@@ -632,7 +768,7 @@ int pick_bn(int64_t M_tiles, int64_t N) {
     return e ? atoi(e) : 0;
   }();
   if (forced == 256 || forced == 160 || forced == 128 || forced == 64) return forced;
-  // fewest padded columns first, then fewest waves (bigger tiles amortise the A reads)
+  const bool pair = cluster_mode() >= 3 && M_tiles >= 2;
   const int cands[4] = {256, 160, 128, 64};
   int best = 64;
   double best_cost = 1e300;
@@ -640,12 +776,11 @@ int pick_bn(int64_t M_tiles, int64_t N) {
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     const int64_t tn = ceil_div(N, bn);
-    const int64_t tiles = M_tiles * tn;
-    const int64_t waves = ceil_div(tiles, sms);
-    // time ~ waves * tile work; narrower tiles re-read A from smem more often per flop
-    // (128 B/clk of operand traffic at BN=128 vs 96 at BN=256), hence the penalty factors
-    // measured on B200 (profiles/r01_kernel_probes_bn.txt): the same work runs 1.3x / 1.45x slower with
-    // 160- / 128-wide tiles than with 256-wide ones (smem operand traffic 115 / 128 vs 96 B/clk)
+    // time ~ waves * tile work.  Every MMA re-reads its 128 rows of A from smem whatever its width, so narrower tiles
+    // move more operand bytes per flop; measured on B200 (profiles/r01_kernel_probes_bn.txt, r01_kernel_probes_pair.txt)
+    // 160- / 128-wide tiles run 1.3x / 1.45x slower per flop than 256-wide ones - in CTA-pair mode as well, where the
+    // B half per CTA shrinks but the A rows do not.
+    const int64_t waves = pair ? ceil_div(ceil_div(M_tiles, 2) * tn, sms / 2) : ceil_div(M_tiles * tn, sms);
     const double penalty = bn == 256 ? 1.0 : (bn == 160 ? 1.3 : (bn == 128 ? 1.45 : 1.8));
     const double cost = double(waves) * (double(bn) * penalty + 24.0);
     if (cost < best_cost) {

@@ -4,6 +4,7 @@
     python tools/kernel_probe.py conv        # 3x3 1280->1280 @ 32x32, batch 16
     python tools/kernel_probe.py attn        # self-attention B=16 H=20 S=1024 d=64
     python tools/kernel_probe.py attn4096    # self-attention B=16 H=10 S=4096 d=64
+    python tools/kernel_probe.py gemm_res | gemm640_res | attn77 | attn77_4096 | attn_sam_win | attn_sam_global
 Also prints CUDA-event timings (L2 flushed between launches)."""
 
 import sys
@@ -40,6 +41,33 @@ elif which == "conv320":
     x = torch.randn(16, 320, 128, 128, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
     w = torch.randn(320, 320, 3, 3, device=dev, dtype=bf) * 0.02
     fn, flops = (lambda: B.conv2d(x, w, None, 1, 1)), 2.0 * 16 * 16384 * 320 * 320 * 9
+elif which == "gemm_kv":  # cross-attention K/V projection of the 77 text tokens, UNet batch 16
+    M, K, N = 1232, 2048, 2560
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
+elif which == "gemm_res":
+    M, K, N = 16384, 1280, 1280
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    b, r = torch.randn(N, device=dev, dtype=bf), torch.randn(M, N, device=dev, dtype=bf)
+    fn, flops = (lambda: B.linear(x, w, b, residual=r)), 2.0 * M * N * K
+elif which == "gemm640_res":
+    M, K, N = 65536, 640, 640
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    b, r = torch.randn(N, device=dev, dtype=bf), torch.randn(M, N, device=dev, dtype=bf)
+    fn, flops = (lambda: B.linear(x, w, b, residual=r)), 2.0 * M * N * K
+elif which in ("attn77", "attn77_4096"):
+    Bn, H, S = (16, 20, 1024) if which == "attn77" else (16, 10, 4096)
+    q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
+    k, v = torch.randn(Bn, 77, H * 64, device=dev, dtype=bf), torch.randn(Bn, 77, H * 64, device=dev, dtype=bf)
+    fn, flops = (lambda: B.sdpa(q, k, v, H)), 4.0 * Bn * H * S * 77 * 64
+elif which == "attn_sam_win":
+    qkv = torch.randn(25, 14, 14, 3 * 1280, device=dev, dtype=bf)
+    rh, rw = torch.randn(27, 80, device=dev, dtype=bf), torch.randn(27, 80, device=dev, dtype=bf)
+    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * 25 * 16 * 196 * 196 * 80
+elif which == "attn_sam_global":
+    qkv = torch.randn(1, 64, 64, 3 * 1280, device=dev, dtype=bf)
+    rh, rw = torch.randn(127, 80, device=dev, dtype=bf), torch.randn(127, 80, device=dev, dtype=bf)
+    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * 16 * 4096 * 4096 * 80
 elif which in ("attn", "attn4096"):
     Bn, H, S = (16, 20, 1024) if which == "attn" else (16, 10, 4096)
     q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
