@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem p) {
   __shared__ float Bs[TK][TN + 1];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = int64_t(blockIdx.y) * TM, n0 = int64_t(blockIdx.x) * TN;
+  const int64_t m0 = int64_t(blockIdx.x) * TM, n0 = int64_t(blockIdx.y) * TN;  // row tiles on x: no 65535 limit
   // columns owned by this thread inside the tile: a value pair and its GEGLU gate pair
   const int cg = (tx >> 3) * 32, cj = (tx & 7) * 2;
   const int cols[4] = {cg + cj, cg + cj + 1, cg + 16 + cj, cg + 16 + cj + 1};
@@ -141,23 +141,8 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmProblem p) {
 
 template <typename T>
 int launch(cudaStream_t st, const GemmProblem& p) {
-  dim3 grid((unsigned)ceil_div(p.N, TN), (unsigned)ceil_div(p.M, TM));
-  if (grid.y > 65535) {
-    // fold the row tiles that exceed the y limit into z-less form: swap roles via chunks
-    GemmProblem q = p;
-    const int64_t chunk = int64_t(65535) * TM;
-    if (p.conv) RB200_FAIL(-3, "simt conv: M=%lld too large for one launch", (long long)p.M);
-    for (int64_t m = 0; m < p.M; m += chunk) {
-      q.M = (p.M - m < chunk) ? (p.M - m) : chunk;
-      q.a = static_cast<const T*>(p.a) + m * p.lda;
-      q.a2 = p.a2 ? static_cast<const T*>(p.a2) + m * p.lda2 : nullptr;
-      q.residual = p.residual ? static_cast<const T*>(p.residual) + m * p.ldr : nullptr;
-      q.y = static_cast<T*>(p.y) + m * p.ldy;
-      int rc = launch<T>(st, q);
-      if (rc) return rc;
-    }
-    return 0;
-  }
+  if (ceil_div(p.N, TN) > 65535 || ceil_div(p.M, TM) > 2147483647LL) RB200_FAIL(-3, "simt gemm: %lld x %lld is too large for one launch", (long long)p.M, (long long)p.N);
+  dim3 grid((unsigned)ceil_div(p.M, TM), (unsigned)ceil_div(p.N, TN));
   if (p.conv)
     simt_gemm_kernel<T, true><<<grid, 256, 0, st>>>(p);
   else
