@@ -64,6 +64,45 @@ def control_lora_test_weights() -> dict[str, torch.Tensor]:
     return sd
 
 
+def pin_controlnet(write: bool) -> None:
+    """SD 1.5 + ControlNet (stable_diffusion_1/controlnet.py): own generator, own fixture file, so that
+    adding it does not disturb the random stream of the other fixtures."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.controlnet import SD1ControlnetAdapter
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+    from safetensors.torch import save_file
+
+    from oracle import unet as ounet
+    from oracle.weights import keyed_state_dict
+
+    print("SD1UNet + Controlnet")
+    gen = torch.Generator().manual_seed(4321)
+    g = lambda *s: torch.randn(*s, generator=gen)
+    with torch.no_grad():
+        unet = SD1UNet(4)
+        adapter = SD1ControlnetAdapter(unet, name="canny", scale=0.9, scale_decay=0.825).inject()
+        shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        sdict = keyed_state_dict(shapes, seed=4)
+        unet.load_state_dict(sdict)
+        x, ts, ctx = g(2, 4, 32, 32), torch.tensor([[500]]), g(2, 77, 768)
+        cond = torch.rand(2, 3, 256, 256, generator=gen)
+        unet.set_timestep(ts); unet.set_clip_text_embedding(ctx)
+        adapter.set_controlnet_condition(cond)
+        y = unet(x)
+        deltas = ounet.sd1_controlnet(sdict, x, ts, ctx, cond, scale=0.9, scale_decay=0.825)
+        _close("SD1UNet + Controlnet", ounet.sd1_unet(sdict, x, ts, ctx, residuals=deltas), y)
+        adapter.eject()
+        unet.set_timestep(ts); unet.set_clip_text_embedding(ctx)  # contexts are reset after every forward
+        y_plain = unet(x)
+        plain = {k: v for k, v in sdict.items() if not k.startswith("Controlnet.")}
+        _close("SD1UNet after eject", ounet.sd1_unet(plain, x, ts, ctx), y_plain)
+    fx = {"cn.x": x, "cn.timestep": ts, "cn.ctx": ctx, "cn.cond": cond, "cn.y": y, "cn.y_plain": y_plain}
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "controlnet.safetensors"))
+        print(f"  wrote {GOLDEN / 'controlnet.safetensors'}")
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -293,4 +332,8 @@ def main(write: bool) -> None:
 
 
 if __name__ == "__main__":
-    main(write="--check" not in sys.argv)
+    if "--only-controlnet" in sys.argv:
+        pin_controlnet(write="--check" not in sys.argv)
+    else:
+        main(write="--check" not in sys.argv)
+        pin_controlnet(write="--check" not in sys.argv)

@@ -101,10 +101,54 @@ _SD1_UP = [(False, False), (False, False), (False, True), (True, False), (True, 
            (True, False), (True, False), (True, True), (True, False), (True, False), (True, False)]
 
 
-def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor) -> Tensor:
+def condition_encoder(sd: SD, prefix: str, image: Tensor) -> Tensor:
+    """ControlNet ConditionEncoder (stable_diffusion_1/controlnet.py:16-68): conv-SiLU stem, three
+    (conv, SiLU, stride-2 conv, SiLU) stages, output conv to 320 channels at 1/8 resolution."""
+    h = ops.silu(_conv(sd, prefix + ".Chain_1.Conv2d", image, padding=1))
+    for i in (2, 3, 4):
+        h = ops.silu(_conv(sd, f"{prefix}.Chain_{i}.Conv2d_1", h, padding=1))
+        h = ops.silu(_conv(sd, f"{prefix}.Chain_{i}.Conv2d_2", h, stride=2, padding=1))
+    return _conv(sd, prefix + ".Conv2d", h, padding=1)
+
+
+def sd1_controlnet(
+    sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, condition: Tensor, scale: float = 1.0,
+    scale_decay: float = 1.0, prefix: str = "Controlnet",
+) -> list[Tensor]:
+    """Controlnet (stable_diffusion_1/controlnet.py:71-173): the UNet encoder + middle block run on
+    the first four latent channels (:103), the encoded condition is added after the input conv
+    (:111-116), and after every one of the 12 down entries and after the middle block a 1x1 conv taps
+    the activation; tap n contributes ``tap * scale * scale_decay ** (12 - n)`` to residual slot n
+    (:153-173).  The taps are Passthroughs: the control copy's own activations are not modified."""
+    dtype = x.dtype
+    temb = range_encoder(sd, prefix + ".TimestepEncoder.RangeEncoder", timestep, dtype)
+    h = x[:, :4]
+    deltas: list[Tensor] = []
+    for i, entry in enumerate(_SD1_DOWN):
+        p = f"{prefix}.DownBlocks.Chain_{i + 1}"
+        if entry[0] == "in":
+            h = _conv(sd, p + ".Conv2d", h, padding=1)
+            h = h + condition_encoder(sd, p + ".Residual.ConditionEncoder", condition)
+        elif entry[0] == "down":
+            h = _conv(sd, p + ".Downsample.Conv2d", h, stride=2, padding=1)
+        else:
+            h = residual_block(sd, p + ".ResidualBlock", h, temb)
+            if entry[1]:
+                h = cross_attention_2d(sd, p + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
+        deltas.append(_conv(sd, p + ".Passthrough.Conv2d", h) * scale * scale_decay ** float(12 - i))
+    m = prefix + ".MiddleBlock"
+    h = residual_block(sd, m + ".ResidualBlock_1", h, temb)
+    h = cross_attention_2d(sd, m + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
+    h = residual_block(sd, m + ".ResidualBlock_2", h, temb)
+    deltas.append(_conv(sd, m + ".Passthrough.Conv2d", h) * scale * scale_decay ** 0.0)
+    return deltas
+
+
+def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, residuals: list[Tensor] | None = None) -> Tensor:
     """SD1UNet forward (stable_diffusion_1/unet.py:165-249): 12 down entries each recording a
-    skip, the middle block (added to the never-written 13th residual slot, i.e. to 0.0), 12 up entries
-    each consuming one skip."""
+    skip, the middle block (added to the 13th residual slot: 0.0 for the plain UNet), 12 up entries
+    each consuming one skip.  ``residuals`` are the 13 ControlNet corrections already sitting in the
+    slots when the UNet runs (the control copy is child 0 of the UNet, controlnet.py:196-203)."""
     dtype = x.dtype
     temb = range_encoder(sd, "TimestepEncoder.RangeEncoder", timestep, dtype)
     skips: list[Tensor] = []
@@ -119,14 +163,16 @@ def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor) -
             h = residual_block(sd, p + ".ResidualBlock", h, temb)
             if entry[1]:
                 h = cross_attention_2d(sd, p + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
-        skips.append(h)  # ResidualAccumulator: residuals[n] = x + 0.0
+        # ResidualAccumulator: residuals[n] = x + residuals[n]; the accumulator is a Passthrough, so the
+        # encoder itself continues from the uncorrected h
+        skips.append(h if residuals is None else h + residuals[i])
     m = "Sum.MiddleBlock"
     mid = residual_block(sd, m + ".ResidualBlock_1", h, temb)
     mid = cross_attention_2d(sd, m + ".CLIPLCrossAttention", mid, clip_text_embedding, 8, 1, False)
     mid = residual_block(sd, m + ".ResidualBlock_2", mid, temb)
     # Sum(UseContext residuals[-1], MiddleBlock): the 13th residual slot is never written by the
     # plain UNet (it exists for ControlNet), so this adds the initial 0.0
-    h = 0.0 + mid
+    h = (0.0 if residuals is None else residuals[12]) + mid
     for n, (attn, up) in enumerate(_SD1_UP):
         p = f"UpBlocks.Chain_{n + 1}"
         h = torch.cat([h, skips[-n - 1]], dim=1)  # ResidualConcatenator(-n-2) over 12 skips + 1 spare slot

@@ -184,7 +184,55 @@ def test_sdxl_control_lora_host():
     check(run_control_lora(unet, adapter, f, "cpu", torch.float32), f["cl.y"], "host")
 
 
+def load_controlnet_unet(device="cpu", dtype=torch.float32):
+    """SD1UNet + SD1ControlnetAdapter('canny', scale 0.9, decay 0.825) with keyed weights (seed 4) - the
+    construction recorded by oracle/pin_against_reference.py::pin_controlnet."""
+    from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1 import SD1ControlnetAdapter
+
+    def build():
+        unet = SD1UNet(4, device="meta")
+        return unet, SD1ControlnetAdapter(unet, name="canny", scale=0.9, scale_decay=0.825).inject()
+
+    unet, adapter = build()
+    shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+    sd = keyed_state_dict(shapes, seed=4)
+    unet.load_state_dict({k: v.to(device, dtype) for k, v in sd.items()}, assign=True)
+    return unet, adapter
+
+
+def run_controlnet(unet, adapter, f, device, dtype):
+    unet.set_timestep(f["cn.timestep"].to(device))
+    unet.set_clip_text_embedding(f["cn.ctx"].to(device, dtype))
+    if adapter is not None:
+        adapter.set_controlnet_condition(f["cn.cond"].to(device, dtype))
+    with no_grad():
+        return unet(f["cn.x"].to(device, dtype))
+
+
+def test_sd1_controlnet_host():
+    """SD 1.5 ControlNet (A16): 13 scaled zero-conv taps into the UNet's residual slots, then eject."""
+    f = load_file(str(GOLDEN / "controlnet.safetensors"))
+    unet, adapter = load_controlnet_unet()
+    before = len(unet.state_dict())
+    check(run_controlnet(unet, adapter, f, "cpu", torch.float32), f["cn.y"], "host")
+    adapter.scale = 0.0  # taps muted: the plain UNet's output
+    check(run_controlnet(unet, adapter, f, "cpu", torch.float32), f["cn.y_plain"], "host")
+    adapter.eject()
+    assert len(unet.state_dict()) == before - 340 and unet.parent is None
+    check(run_controlnet(unet, None, f, "cpu", torch.float32), f["cn.y_plain"], "host")
+
+
 # ------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_sd1_controlnet_gpu(cuda_device, dtype):
+    f = load_file(str(GOLDEN / "controlnet.safetensors"))
+    unet, adapter = load_controlnet_unet(device=cuda_device, dtype=dtype)
+    check(run_controlnet(unet, adapter, f, cuda_device, dtype), f["cn.y"], dtype)
+    adapter.eject()
+    check(run_controlnet(unet, None, f, cuda_device, dtype), f["cn.y_plain"], dtype)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=str)
 @pytest.mark.parametrize("fusion", [True, False], ids=["fused", "unfused"])

@@ -89,6 +89,21 @@ def test_sd1_unet_full():
     close(ounet.sd1_unet(sd, f["sd1.x"], f["sd1.timestep"], f["sd1.ctx"]), f["sd1.y"], rel=2e-5)
 
 
+def test_sd1_controlnet_full():
+    """Oracle restatement of SD 1.5 + ControlNet (13 scaled taps into the residual slots) against the
+    reference's recorded output, and the plain UNet after eject."""
+    from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1 import SD1ControlnetAdapter, SD1UNet
+
+    f = load_file(str(GOLDEN / "controlnet.safetensors"))
+    unet = SD1UNet(4, device="meta")
+    SD1ControlnetAdapter(unet, name="canny").inject()
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=4)
+    deltas = ounet.sd1_controlnet(sd, f["cn.x"], f["cn.timestep"], f["cn.ctx"], f["cn.cond"], scale=0.9, scale_decay=0.825)
+    assert len(deltas) == 13
+    close(ounet.sd1_unet(sd, f["cn.x"], f["cn.timestep"], f["cn.ctx"], residuals=deltas), f["cn.y"], rel=2e-5)
+    close(ounet.sd1_unet(sd, f["cn.x"], f["cn.timestep"], f["cn.ctx"]), f["cn.y_plain"], rel=2e-5)
+
+
 def test_fast_mode_matches_golden():
     """oracle.ops.FAST (the fused ATen CPU calls the reference itself makes; used only for the timed
     CPU baseline) is pinned to the same golden vectors."""
