@@ -116,6 +116,13 @@ int rb200_conv2d(void* stream, int dtype, const void* x, const void* w_packed, c
                  int64_t W, int64_t Cin, int64_t Cout, int R, int S, int stride, int pad,
                  int epilogue);
 
+/* Zero-pad the channels of an image to a multiple of 8 so that narrow input convolutions (the UNet's
+ * 4-channel latent conv, latent_diffusion/stable_diffusion_xl/unet.py:258-351; the 3-channel
+ * ConditionEncoder stem, stable_diffusion_1/controlnet.py:16-68) run on the tensor-core path with
+ * zero-extended weights: y[B,H,W,Cp] (dense NHWC) = x[B,C,H,W] addressed through element strides. */
+int rb200_pad_channels(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C,
+                       int Cp, int64_t sb, int64_t sc, int64_t sh, int64_t sw);
+
 /* ---- GroupNorm (+SiLU) ----------------------------------------------------------------------
  * Replaces fluxion/layers/norm.py:52-92 (+ activations.py:31-41 when silu != 0).
  * x, y: NHWC [B, HW, C]; statistics per (sample, group) over HW * C/G elements in fp32.

@@ -80,6 +80,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_sam_attention_workspace_bytes": (_Z, [_L, _I, _I, _I, _I]),
     "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
     "rb200_patchify": (_I, [_P, _I, _P, _P, _L, _L, _L, _L, _I, _L, _L, _L, _L]),
+    "rb200_pad_channels": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _L, _L, _L, _L]),
     "rb200_window_partition": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
 }
 
@@ -206,6 +207,7 @@ class _PackCache:
 
 
 _conv_cache = _PackCache()
+_conv_pad_cache = _PackCache()
 _patch_cache = _PackCache()
 _geglu_cache = _PackCache()
 _lora_cache = _PackCache()
@@ -470,6 +472,20 @@ def _patchify_impl(x: Tensor, patch: int) -> Tensor:
     return y
 
 
+def _pad_channels_impl(x: Tensor, cp: int) -> Tensor:
+    lib = load_library()
+    B, C, H, W = x.shape
+    y = torch.empty((B, cp, H, W), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if y.numel():
+        _check(
+            lib.rb200_pad_channels(
+                _stream(), _dtype_code(x), x.data_ptr(), y.data_ptr(), B, H, W, C, cp,
+                x.stride(0), x.stride(1), x.stride(2), x.stride(3),
+            )
+        )
+    return y
+
+
 def _window_partition_impl(x: Tensor, window: int) -> Tensor:
     lib = load_library()
     B, H, W, C = x.shape
@@ -515,6 +531,7 @@ _torch_lib.define(
 )
 _torch_lib.define("sam_attention(Tensor qkv, Tensor rel_h, Tensor rel_w, int heads) -> Tensor")
 _torch_lib.define("patchify(Tensor x, int patch) -> Tensor")
+_torch_lib.define("pad_channels(Tensor x, int cp) -> Tensor")
 _torch_lib.define("window_partition(Tensor x, int window) -> Tensor")
 _torch_lib.define("window_merge(Tensor x, int window, int height, int width) -> Tensor")
 
@@ -529,6 +546,7 @@ for _name, _fn in (
     ("sdpa", _sdpa_impl),
     ("sam_attention", _sam_attention_impl),
     ("patchify", _patchify_impl),
+    ("pad_channels", _pad_channels_impl),
     ("window_partition", _window_partition_impl),
     ("window_merge", _window_merge_impl),
 ):
@@ -586,6 +604,11 @@ def _sam_attention_fake(qkv, rel_h, rel_w, heads):  # type: ignore[no-untyped-de
 def _patchify_fake(x, patch):  # type: ignore[no-untyped-def]
     B, C, H, W = x.shape
     return x.new_empty((B * (H // patch) * (W // patch), patch * patch * C))
+
+
+@torch.library.register_fake("refiners_b200::pad_channels")
+def _pad_channels_fake(x, cp):  # type: ignore[no-untyped-def]
+    return x.new_empty((x.shape[0], cp, x.shape[2], x.shape[3]))
 
 
 @torch.library.register_fake("refiners_b200::window_partition")
@@ -692,16 +715,23 @@ def geglu_fusable(weight: Tensor) -> bool:
     return weight.dtype in (torch.bfloat16, torch.float16) and (weight.shape[0] // 2) % 16 == 0 and weight.shape[1] % 8 == 0
 
 
-def packed_conv_weight(weight: Tensor) -> Tensor:
+def packed_conv_weight(weight: Tensor, cin_padded: int | None = None) -> Tensor:
+    """[Cout, Cin, R, S] -> [R*S, Cout, Cin] (cached per weight object); with ``cin_padded`` the input-channel
+    axis is zero-extended to that width (pairs with ``pad_channels`` on the activation)."""
+    cache = _conv_cache if cin_padded is None else _conv_pad_cache
     key = _PackCache.key(weight)
-    packed = _conv_cache.get(key, (weight,))
+    packed = cache.get(key, (weight,))
     if packed is None:
         lib = load_library()
         w = weight.contiguous()
         Cout, Cin, R, S = w.shape
         packed = torch.empty((R * S, Cout, Cin), device=w.device, dtype=w.dtype)
         _check(lib.rb200_conv2d_pack_weight(_stream(), _dtype_code(w), w.data_ptr(), packed.data_ptr(), Cout, Cin, R, S))
-        _conv_cache.put(key, (weight,), packed)
+        if cin_padded is not None:
+            wide = torch.zeros((R * S, Cout, cin_padded), device=w.device, dtype=w.dtype)
+            wide[:, :, :Cin] = packed
+            packed = wide
+        cache.put(key, (weight,), packed)
     return packed
 
 
@@ -731,6 +761,11 @@ def conv2d(
         Bn, _, H, W = x.shape
         y = _ops.linear(_ops.patchify(x, R), patch_gemm_weight(weight), bias, None, None, None, None, epilogue)
         return y.view(Bn, H // R, W // R, weight.shape[0]).permute(0, 3, 1, 2)
+    cin = weight.shape[1]
+    if cin % 8 != 0 and x.dtype in (torch.bfloat16, torch.float16):
+        # narrow input convs (4 latent channels, 3 image channels): zero-extend to 8 channels for the tcgen05 path
+        cp = (cin + 7) // 8 * 8
+        return _ops.conv2d(_ops.pad_channels(x, cp), packed_conv_weight(weight, cp), bias, chan_bias, residual, R, S, stride, padding, epilogue)
     return _ops.conv2d(x, packed_conv_weight(weight), bias, chan_bias, residual, R, S, stride, padding, epilogue)
 
 

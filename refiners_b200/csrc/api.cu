@@ -42,6 +42,7 @@ int add_impl(cudaStream_t, int, const void*, const void*, void*, int64_t, float)
 int geglu_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t);
 int patchify_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t);
 int window_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
+int pad_channels_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, int64_t);
 int conv_pack_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int, int);
 int geglu_pack_impl(cudaStream_t, int, const void*, const void*, void*, void*, int64_t, int64_t);
 int lora_pack_impl(cudaStream_t, int, int, const rb200_lora*, int64_t, int64_t, void*, void*, float*, int);
@@ -199,6 +200,14 @@ int rb200_add(void* stream, int dtype, const void* a, const void* b, void* y, in
   if (bad_dtype(dtype) || !a || !b || !y) RB200_FAIL(-1, "add: bad arguments");
   if (n <= 0) return 0;
   return add_impl(static_cast<cudaStream_t>(stream), dtype, a, b, y, n, alpha);
+}
+
+int rb200_pad_channels(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int Cp, int64_t sb, int64_t sc,
+                       int64_t sh, int64_t sw) {
+  if (bad_dtype(dtype) || !x || !y) RB200_FAIL(-1, "pad_channels: bad arguments");
+  if (H < 1 || W < 1 || C < 1) RB200_FAIL(-1, "pad_channels: bad geometry");
+  if (B <= 0) return 0;
+  return pad_channels_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, H, W, C, Cp, sb, sc, sh, sw);
 }
 
 int rb200_patchify(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, int P, int64_t sb,

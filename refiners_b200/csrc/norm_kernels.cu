@@ -345,6 +345,32 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
   }
 }
 
+// Channel padding for the tensor-core conv (needs Cin % 8 == 0): y[b, h, w, 0..Cp) = x[b, 0..C, h, w] then zeros.
+// x is addressed through element strides (NCHW or channels-last), y is dense NHWC; one thread per output pixel-vector.
+template <typename T>
+__global__ void pad_channels_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t pixels, int H, int W, int C, int Cp, int64_t sb,
+                                    int64_t sc, int64_t sh, int64_t sw) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = Cp / V;
+  const int64_t total = pixels * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int v = int(idx % cv);
+    const int64_t pix = idx / cv;
+    const int w = int(pix % W);
+    const int h = int((pix / W) % H);
+    const int64_t b = pix / (int64_t(W) * H);
+    const T* src = x + b * sb + int64_t(h) * sh + int64_t(w) * sw;
+    Vec16<T> val;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const int c = v * V + e;
+      val.v[e] = c < C ? src[int64_t(c) * sc] : from_f<T>(0.f);
+    }
+    st16(y + pix * Cp + v * V, val);
+  }
+}
+
 // Non-overlapping P x P patches of an image as GEMM rows: y[(b, ho, wo), (r, s, c)] = x[b, c, ho P + r, wo P + s]
 // (x addressed through element strides, so NCHW and channels-last inputs both work without a layout copy).
 template <typename T>
@@ -583,6 +609,19 @@ int geglu_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows,
     geglu_kernel<T><<<ew_grid(rows * F / V + 1), 256, 0, st>>>((const T*)x, (T*)y, rows, F, vec_ok);
   });
   RB200_CHECK_LAUNCH("geglu");
+  return 0;
+}
+
+int pad_channels_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int Cp, int64_t sb, int64_t sc,
+                      int64_t sh, int64_t sw) {
+  if (!aligned16(y)) RB200_FAIL(-1, "pad_channels: output must be 16-byte aligned");
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    if (Cp % V != 0 || Cp < C) RB200_FAIL(-1, "pad_channels: Cp=%d must be >= C=%d and a multiple of %d", Cp, C, V);
+    const int64_t pixels = B * H * W;
+    pad_channels_kernel<T><<<ew_grid(pixels * (Cp / V)), 256, 0, st>>>((const T*)x, (T*)y, pixels, H, W, C, Cp, sb, sc, sh, sw);
+  });
+  RB200_CHECK_LAUNCH("pad_channels");
   return 0;
 }
 

@@ -128,7 +128,9 @@ CONV_CASES = [
     (1, 320, 32, 32, 320, 3, 1, 1),
     (2, 320, 32, 32, 640, 1, 1, 0),
     (2, 64, 32, 32, 64, 3, 2, 1),     # Downsample (sampling.py:41-98)
-    (2, 4, 32, 32, 320, 3, 1, 1),     # UNet input conv: Cin = 4 -> CUDA-core path
+    (2, 4, 32, 32, 320, 3, 1, 1),     # UNet input conv: Cin = 4 -> channels zero-extended to 8 for the tcgen05 path
+    (1, 3, 40, 24, 16, 3, 1, 1),      # ConditionEncoder stem: Cin = 3, Cout = 16
+    (2, 12, 16, 16, 32, 3, 2, 1),     # Cin = 12 -> 16, stride 2
     (2, 320, 16, 16, 4, 3, 1, 1),     # UNet output conv: Cout = 4
     (4, 128, 8, 8, 128, 3, 1, 1),     # 8x8 map: one tile spans two images
     (1, 96, 24, 40, 80, 3, 1, 1),     # odd geometry
