@@ -160,6 +160,18 @@ int rb200_patchify(void* stream, int dtype, const void* x, void* y, int64_t B, i
 int rb200_window_partition(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W,
                            int C, int window, int merge);
 
+/* ---- UNet skip-connection plumbing -------------------------------------------------------------
+ * Channel concatenation of n <= 4 channels-last maps: y[p, :] = cat(src_0[p, :], ..., src_{n-1}[p, :]) for
+ * `pixels` = B*H*W rows.  Replaces fluxion/layers/chain.py:930-964 (Concatenate, dim = 1) as used by
+ * latent_diffusion/unet.py:66-79 (ResidualConcatenator).  srcs / channels are HOST arrays. */
+int rb200_concat_channels(void* stream, int dtype, int n, const void* const* srcs, const int* channels,
+                          void* y, int64_t pixels);
+/* Nearest-neighbour resize of a channels-last map, x[B,H,W,C] -> y[B,Ho,Wo,C], source index
+ * min(floor(dst * in / out), in - 1): fluxion/layers/sampling.py:13-38 (Interpolate, mode "nearest"),
+ * the 2x upsampling of sampling.py:101-161 (Upsample). */
+int rb200_resize_nearest(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C,
+                         int Ho, int Wo);
+
 /* ---- Scaled dot-product attention -----------------------------------------------------------
  * Replaces fluxion/layers/attentions.py:115-202 (split heads, F.scaled_dot_product_attention,
  * merge heads).  q[B,Sq,H,D], k/v[B,Sk,H,D], o[B,Sq,H,D] addressed through (batch, seq)

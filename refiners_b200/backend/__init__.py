@@ -81,6 +81,8 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
     "rb200_patchify": (_I, [_P, _I, _P, _P, _L, _L, _L, _L, _I, _L, _L, _L, _L]),
     "rb200_pad_channels": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _L, _L, _L, _L]),
+    "rb200_concat_channels": (_I, [_P, _I, _I, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _P, _L]),
+    "rb200_resize_nearest": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
     "rb200_window_partition": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
 }
 
@@ -486,6 +488,33 @@ def _pad_channels_impl(x: Tensor, cp: int) -> Tensor:
     return y
 
 
+def _concat_channels_impl(parts: list[Tensor]) -> Tensor:
+    lib = load_library()
+    _same(*parts)
+    B, _, H, W = parts[0].shape
+    srcs = [p.contiguous(memory_format=torch.channels_last) for p in parts]
+    for p in srcs:
+        if p.shape[0] != B or p.shape[2] != H or p.shape[3] != W:
+            raise BackendError(f"concat_channels: shapes differ outside the channel axis: {[tuple(t.shape) for t in parts]}")
+    ct = sum(p.shape[1] for p in srcs)
+    y = torch.empty((B, ct, H, W), device=parts[0].device, dtype=parts[0].dtype, memory_format=torch.channels_last)
+    if y.numel():
+        ptrs = (ctypes.c_void_p * len(srcs))(*[p.data_ptr() for p in srcs])
+        chans = (ctypes.c_int * len(srcs))(*[p.shape[1] for p in srcs])
+        _check(lib.rb200_concat_channels(_stream(), _dtype_code(y), len(srcs), ptrs, chans, y.data_ptr(), B * H * W))
+    return y
+
+
+def _resize_nearest_impl(x: Tensor, height: int, width: int) -> Tensor:
+    lib = load_library()
+    B, C, H, W = x.shape
+    xc = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, C, height, width), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if y.numel():
+        _check(lib.rb200_resize_nearest(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), B, H, W, C, height, width))
+    return y
+
+
 def _window_partition_impl(x: Tensor, window: int) -> Tensor:
     lib = load_library()
     B, H, W, C = x.shape
@@ -532,6 +561,8 @@ _torch_lib.define(
 _torch_lib.define("sam_attention(Tensor qkv, Tensor rel_h, Tensor rel_w, int heads) -> Tensor")
 _torch_lib.define("patchify(Tensor x, int patch) -> Tensor")
 _torch_lib.define("pad_channels(Tensor x, int cp) -> Tensor")
+_torch_lib.define("concat_channels(Tensor[] parts) -> Tensor")
+_torch_lib.define("resize_nearest(Tensor x, int height, int width) -> Tensor")
 _torch_lib.define("window_partition(Tensor x, int window) -> Tensor")
 _torch_lib.define("window_merge(Tensor x, int window, int height, int width) -> Tensor")
 
@@ -547,6 +578,8 @@ for _name, _fn in (
     ("sam_attention", _sam_attention_impl),
     ("patchify", _patchify_impl),
     ("pad_channels", _pad_channels_impl),
+    ("concat_channels", _concat_channels_impl),
+    ("resize_nearest", _resize_nearest_impl),
     ("window_partition", _window_partition_impl),
     ("window_merge", _window_merge_impl),
 ):
@@ -609,6 +642,17 @@ def _patchify_fake(x, patch):  # type: ignore[no-untyped-def]
 @torch.library.register_fake("refiners_b200::pad_channels")
 def _pad_channels_fake(x, cp):  # type: ignore[no-untyped-def]
     return x.new_empty((x.shape[0], cp, x.shape[2], x.shape[3]))
+
+
+@torch.library.register_fake("refiners_b200::concat_channels")
+def _concat_channels_fake(parts):  # type: ignore[no-untyped-def]
+    p0 = parts[0]
+    return p0.new_empty((p0.shape[0], sum(p.shape[1] for p in parts), p0.shape[2], p0.shape[3]))
+
+
+@torch.library.register_fake("refiners_b200::resize_nearest")
+def _resize_nearest_fake(x, height, width):  # type: ignore[no-untyped-def]
+    return x.new_empty((x.shape[0], x.shape[1], height, width))
 
 
 @torch.library.register_fake("refiners_b200::window_partition")
@@ -777,6 +821,31 @@ def patch_gemm_weight(weight: Tensor) -> Tensor:
         packed = weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous()
         _patch_cache.put(key, (weight,), packed)
     return packed
+
+
+def concat_channels_supported(parts: Sequence[Any]) -> bool:
+    """dim-1 concatenation of 2..4 same-dtype 4-D CUDA maps whose channel counts fill whole 16-byte vectors."""
+    if not 2 <= len(parts) <= 4 or not all(isinstance(p, Tensor) and p.is_cuda and p.ndim == 4 for p in parts):
+        return False
+    p0 = parts[0]
+    if p0.dtype not in _DT or any(p.dtype != p0.dtype or p.device != p0.device for p in parts):
+        return False
+    vec = 16 // p0.element_size()
+    return all(p.shape[1] % vec == 0 and p.shape[0] == p0.shape[0] and p.shape[2:] == p0.shape[2:] for p in parts)
+
+
+def concat_channels(parts: Sequence[Tensor]) -> Tensor:
+    _inference_only(*parts)
+    return _ops.concat_channels(list(parts))
+
+
+def resize_nearest_supported(x: Tensor) -> bool:
+    return x.is_cuda and x.ndim == 4 and x.dtype in _DT and x.shape[1] % (16 // x.element_size()) == 0
+
+
+def resize_nearest(x: Tensor, height: int, width: int) -> Tensor:
+    _inference_only(x)
+    return _ops.resize_nearest(x, int(height), int(width))
 
 
 def window_partition(x: Tensor, window: int) -> Tensor:

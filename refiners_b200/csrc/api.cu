@@ -43,6 +43,8 @@ int geglu_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t);
 int patchify_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t);
 int window_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
 int pad_channels_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, int64_t);
+int concat_channels_impl(cudaStream_t, int, int, const void* const*, const int*, void*, int64_t);
+int resize_nearest_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
 int conv_pack_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int, int);
 int geglu_pack_impl(cudaStream_t, int, const void*, const void*, void*, void*, int64_t, int64_t);
 int lora_pack_impl(cudaStream_t, int, int, const rb200_lora*, int64_t, int64_t, void*, void*, float*, int);
@@ -208,6 +210,19 @@ int rb200_pad_channels(void* stream, int dtype, const void* x, void* y, int64_t 
   if (H < 1 || W < 1 || C < 1) RB200_FAIL(-1, "pad_channels: bad geometry");
   if (B <= 0) return 0;
   return pad_channels_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, H, W, C, Cp, sb, sc, sh, sw);
+}
+
+int rb200_concat_channels(void* stream, int dtype, int n, const void* const* srcs, const int* channels, void* y, int64_t pixels) {
+  if (bad_dtype(dtype) || !srcs || !channels || !y) RB200_FAIL(-1, "concat_channels: bad arguments");
+  if (pixels <= 0) return 0;
+  return concat_channels_impl(static_cast<cudaStream_t>(stream), dtype, n, srcs, channels, y, pixels);
+}
+
+int rb200_resize_nearest(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int Ho, int Wo) {
+  if (bad_dtype(dtype) || !x || !y) RB200_FAIL(-1, "resize_nearest: bad arguments");
+  if (H < 1 || W < 1 || C < 1 || Ho < 1 || Wo < 1) RB200_FAIL(-1, "resize_nearest: bad geometry");
+  if (B <= 0) return 0;
+  return resize_nearest_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, H, W, C, Ho, Wo);
 }
 
 int rb200_patchify(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t H, int64_t W, int64_t C, int P, int64_t sb,

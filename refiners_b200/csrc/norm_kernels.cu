@@ -28,19 +28,32 @@ __global__ void gn_partial_kernel(const T* __restrict__ x, float* __restrict__ p
 #pragma unroll
   for (int e = 0; e < V; ++e) s[e] = q[e] = 0.f;
   const T* base = x + (int64_t(b) * HW) * C + int64_t(v) * V;
-  for (int64_t p = p0 + lane; p < p1; p += lanes) {
-    T vals[V];
-    if constexpr (V * sizeof(T) == 16) {
-      *reinterpret_cast<uint4*>(vals) = *reinterpret_cast<const uint4*>(base + p * C);
-    } else {
+  constexpr int U = 4;  // pixels in flight per thread: four independent 16-byte loads hide the HBM latency
+  for (int64_t p = p0 + lane; p < p1; p += int64_t(lanes) * U) {
+    T vals[U][V];
 #pragma unroll
-      for (int e = 0; e < V; ++e) vals[e] = base[p * C + e];
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + int64_t(u) * lanes;
+      if (pu < p1) {
+        if constexpr (V * sizeof(T) == 16) {
+          *reinterpret_cast<uint4*>(vals[u]) = *reinterpret_cast<const uint4*>(base + pu * C);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) vals[u][e] = base[pu * C + e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) vals[u][e] = from_f<T>(0.f);
+      }
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float f = to_f(vals[e]);
-      s[e] += f;
-      q[e] = fmaf(f, f, q[e]);
+    for (int u = 0; u < U; ++u) {  // fixed order u = 0..3: the sums are run-to-run deterministic
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float f = to_f(vals[u][e]);
+        s[e] += f;
+        q[e] = fmaf(f, f, q[e]);
+      }
     }
   }
 #pragma unroll
@@ -107,37 +120,48 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
     sm[G + g] = stats[(int64_t(b) * G + g) * 2 + 1];
   }
   __syncthreads();
-  float ga[V], be[V], mu[V], rs[V];
+  float sc[V], be[V], mu[V];  // y = (x - mean) * (rstd * gamma) + beta
 #pragma unroll
   for (int e = 0; e < V; ++e) {
     const int c = v * V + e;
-    ga[e] = to_f(gamma[c]);
+    sc[e] = sm[G + c / cpg] * to_f(gamma[c]);
     be[e] = to_f(beta[c]);
     mu[e] = sm[c / cpg];
-    rs[e] = sm[G + c / cpg];
   }
   const int64_t p0 = int64_t(chunk) * GN_PIX;
   const int64_t p1 = (p0 + GN_PIX < HW) ? p0 + GN_PIX : HW;
   const int64_t base = (int64_t(b) * HW) * C + int64_t(v) * V;
-  for (int64_t p = p0 + lane; p < p1; p += lanes) {
-    T vals[V];
-    if constexpr (V * sizeof(T) == 16) {
-      *reinterpret_cast<uint4*>(vals) = *reinterpret_cast<const uint4*>(x + base + p * C);
-    } else {
+  constexpr int U = 4;  // pixels in flight per thread
+  for (int64_t p = p0 + lane; p < p1; p += int64_t(lanes) * U) {
+    T vals[U][V];
 #pragma unroll
-      for (int e = 0; e < V; ++e) vals[e] = x[base + p * C + e];
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + int64_t(u) * lanes;
+      if (pu < p1) {
+        if constexpr (V * sizeof(T) == 16) {
+          *reinterpret_cast<uint4*>(vals[u]) = *reinterpret_cast<const uint4*>(x + base + pu * C);
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) vals[u][e] = x[base + pu * C + e];
+        }
+      }
     }
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      float f = (to_f(vals[e]) - mu[e]) * rs[e] * ga[e] + be[e];
-      if (silu) f = silu_f(f);
-      vals[e] = from_f<T>(f);
-    }
-    if constexpr (V * sizeof(T) == 16) {
-      *reinterpret_cast<uint4*>(y + base + p * C) = *reinterpret_cast<const uint4*>(vals);
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const int64_t pu = p + int64_t(u) * lanes;
+      if (pu >= p1) break;
 #pragma unroll
-      for (int e = 0; e < V; ++e) y[base + p * C + e] = vals[e];
+      for (int e = 0; e < V; ++e) {
+        float f = fmaf(to_f(vals[u][e]) - mu[e], sc[e], be[e]);
+        if (silu) f = sizeof(T) == 2 ? silu_fast(f) : silu_f(f);
+        vals[u][e] = from_f<T>(f);
+      }
+      if constexpr (V * sizeof(T) == 16) {
+        *reinterpret_cast<uint4*>(y + base + pu * C) = *reinterpret_cast<const uint4*>(vals[u]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[base + pu * C + e] = vals[u][e];
+      }
     }
   }
 }
@@ -342,6 +366,55 @@ __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* 
       y[j] = from_f<T>(fmaf(alpha, to_f(b[j]), to_f(a[j])));
   } else {
     for (; i < n; i += stride) y[i] = from_f<T>(fmaf(alpha, to_f(b[i]), to_f(a[i])));
+  }
+}
+
+// Channel concatenation of up to four NHWC maps (the UNet's skip connections, latent_diffusion/unet.py:66-79) and
+// nearest-neighbour resize (layers/sampling.py:13-38), both as one pass of 16-byte vector copies.
+struct CatSources {
+  const void* src[4];
+  int channels[4];
+  int n;
+};
+
+template <typename T>
+__global__ void concat_channels_kernel(const CatSources cs, T* __restrict__ y, int64_t pixels, int Ct) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = Ct / V;
+  const int64_t total = pixels * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    int c = int(idx % cv) * V;
+    const int64_t pix = idx / cv;
+    int which = 0;
+    while (which < cs.n - 1 && c >= cs.channels[which]) {
+      c -= cs.channels[which];
+      ++which;
+    }
+    const T* src = static_cast<const T*>(cs.src[which]) + pix * cs.channels[which] + c;
+    st16(y + idx * V, ld16(src));
+  }
+}
+
+template <typename T>
+__global__ void resize_nearest_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t B, int H, int W, int C, int Ho, int Wo,
+                                      float scale_h, float scale_w) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V;
+  const int64_t total = B * Ho * Wo * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int v = int(idx % cv);
+    int64_t t = idx / cv;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const int64_t b = t / Ho;
+    // ATen's legacy "nearest": src = min(floor(dst * in / out), in - 1), computed in float
+    int hi = int(floorf(float(ho) * scale_h)), wi = int(floorf(float(wo) * scale_w));
+    hi = hi < H - 1 ? hi : H - 1;
+    wi = wi < W - 1 ? wi : W - 1;
+    st16(y + idx * V, ld16(x + ((b * H + hi) * W + wi) * C + v * V));
   }
 }
 
@@ -609,6 +682,40 @@ int geglu_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows,
     geglu_kernel<T><<<ew_grid(rows * F / V + 1), 256, 0, st>>>((const T*)x, (T*)y, rows, F, vec_ok);
   });
   RB200_CHECK_LAUNCH("geglu");
+  return 0;
+}
+
+int concat_channels_impl(cudaStream_t st, int dtype, int n, const void* const* srcs, const int* channels, void* y, int64_t pixels) {
+  if (n < 1 || n > 4) RB200_FAIL(-1, "concat_channels: 1..4 sources, got %d", n);
+  CatSources cs{};
+  cs.n = n;
+  int ct = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!srcs[i] || !aligned16(srcs[i])) RB200_FAIL(-1, "concat_channels: source %d is null or not 16-byte aligned", i);
+    cs.src[i] = srcs[i];
+    cs.channels[i] = channels[i];
+    ct += channels[i];
+  }
+  if (!aligned16(y)) RB200_FAIL(-1, "concat_channels: output must be 16-byte aligned");
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    for (int i = 0; i < n; ++i)
+      if (channels[i] % V != 0) RB200_FAIL(-1, "concat_channels: channel count %d is not a multiple of %d", channels[i], V);
+    concat_channels_kernel<T><<<ew_grid(pixels * (ct / V)), 256, 0, st>>>(cs, (T*)y, pixels, ct);
+  });
+  RB200_CHECK_LAUNCH("concat_channels");
+  return 0;
+}
+
+int resize_nearest_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int Ho, int Wo) {
+  if (!aligned16(x) || !aligned16(y)) RB200_FAIL(-1, "resize_nearest: buffers must be 16-byte aligned");
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    if (C % V != 0) RB200_FAIL(-1, "resize_nearest: C=%d must be a multiple of %d", C, V);
+    resize_nearest_kernel<T><<<ew_grid(B * Ho * Wo * (C / V)), 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, Ho, Wo, float(H) / float(Ho),
+                                                                             float(W) / float(Wo));
+  });
+  RB200_CHECK_LAUNCH("resize_nearest");
   return 0;
 }
 

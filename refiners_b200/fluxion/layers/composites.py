@@ -12,6 +12,7 @@ from torch.nn import functional as F
 
 import torch
 
+from refiners_b200 import backend as B
 from refiners_b200.fluxion.context import Contexts
 from refiners_b200.fluxion.layers.base import Module
 from refiners_b200.fluxion.layers.graph import Chain, Distribute, Lambda, Parallel, SetContext, UseContext
@@ -156,6 +157,8 @@ class Interpolate(Module):
         self.antialias = antialias
 
     def forward(self, x: Tensor, shape: Size) -> Tensor:
+        if self.mode == "nearest" and len(shape) == 2 and B.resize_nearest_supported(x):
+            return B.resize_nearest(x, int(shape[0]), int(shape[1]))
         return interpolate(x, size=shape, mode=self.mode, antialias=self.antialias)
 
 

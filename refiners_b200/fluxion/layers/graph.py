@@ -561,8 +561,13 @@ class Concatenate(Chain):
         self.dim = dim
 
     def forward(self, *args: Any) -> Tensor:
-        parts = [layer(*args) for layer in self._modules.values()]
-        return torch.cat([p for p in parts if p is not None], dim=self.dim)
+        parts = [p for p in (layer(*args) for layer in self._modules.values()) if p is not None]
+        if self.dim == 1 and len(parts) > 1 and isinstance(parts[0], Tensor) and parts[0].is_cuda:
+            from refiners_b200 import backend as B
+
+            if B.concat_channels_supported(parts):
+                return B.concat_channels(parts)  # skip connections: one vectorised channels-last pass
+        return torch.cat(parts, dim=self.dim)
 
     def _show_only_tag(self) -> bool:
         return type(self) is Concatenate

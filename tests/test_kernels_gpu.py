@@ -175,6 +175,25 @@ def test_window_partition_merge(cuda_device, dtype, geom):
     assert torch.equal(back.cpu(), x)
 
 
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+def test_concat_channels_and_resize_nearest(cuda_device, dtype):
+    """Skip-connection plumbing of the UNet: Concatenate(dim=1) (chain.py:930-964 in the reference) and the
+    nearest-neighbour Interpolate (sampling.py:13-38) - pure data movement, bit exact."""
+    from refiners_b200 import backend as B
+    import refiners_b200.fluxion.layers as fl
+
+    a, b, c = _gen((2, 64, 9, 7), 50).to(dtype), _gen((2, 32, 9, 7), 51).to(dtype), _gen((2, 8, 9, 7), 52).to(dtype)
+    dev = lambda t: t.to(cuda_device).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        y = B.concat_channels([dev(a), dev(b), dev(c)])
+        z = fl.Concatenate(fl.Identity(), fl.Identity(), dim=1)(dev(a))
+    assert torch.equal(y.cpu(), torch.cat([a, b, c], dim=1)) and torch.equal(z.cpu(), torch.cat([a, a], dim=1))
+    for size in ((18, 14), (13, 20), (9, 7), (4, 3)):
+        with torch.no_grad():
+            r = fl.Interpolate()(dev(a), torch.Size(size))
+        assert torch.equal(r.cpu(), F.interpolate(a.float(), size=size, mode="nearest").to(dtype)), size
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=str)
 def test_conv2d_fused_terms(cuda_device, kernel_mode, dtype):
     """conv + per-sample channel bias (RangeAdapter2d) + residual (ResidualBlock shortcut)."""
