@@ -73,6 +73,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// no memory to publish (the arriving thread only finished reading TMEM / smem): skips the MEMBAR of a release arrive
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -366,7 +370,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
           }
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_sfree[buf]);  // the tensor core may overwrite this S buffer
+          if (lane == 0) mbar_arrive_relaxed(&bar_sfree[buf]);  // the tensor core may overwrite this S buffer
           const int valid = int((Sk - int64_t(j) * KT) < KT ? (Sk - int64_t(j) * KT) : KT);
           float alpha, psum = 0.f;
           uint32_t packed[KT / 2];
@@ -399,7 +403,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             }
             if (j == ntiles - 1) {  // last read of this work item's bias block
               __syncwarp();
-              if (lane == 0) mbar_arrive(bias_empty);
+              if (lane == 0) mbar_arrive_relaxed(bias_empty);
             }
             float tmax = s[0];
 #pragma unroll

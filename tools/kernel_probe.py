@@ -29,6 +29,11 @@ elif which == "gemm_ff":
     M, K, N = 16384, 1280, 10240
     x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
     fn, flops = (lambda: B.linear(x, w)), 2.0 * M * N * K
+elif which == "gemm_geglu":  # Linear 1280 -> 10240 + GLU(GeLU): the largest single item of the SDXL step
+    M, K, N = 16384, 1280, 10240
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    b = torch.randn(N, device=dev, dtype=bf)
+    fn, flops = (lambda: B.linear_geglu(x, w, b)), 2.0 * M * N * K
 elif which == "gemm640":
     M, K, N = 65536, 640, 640
     x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
