@@ -107,12 +107,12 @@ class Controlnet(fl.Passthrough):
         return fl.Passthrough(fl.Conv2d(channels, channels, kernel_size=1, **kw), fl.Lambda(self._accumulate_into(n)))
 
     def _accumulate_into(self, n: int):
-        def accumulate(x: Tensor) -> Tensor:
+        def _store_residual(x: Tensor) -> Tensor:  # the name shows in repr(): Lambda(_store_residual(x))
             residuals = self.use_context("unet")["residuals"]
             residuals[n] = residuals[n] + x * self.scale * self.scale_decays[n]
             return x
 
-        return accumulate
+        return _store_residual
 
     @property
     def scale_decay(self) -> float:
