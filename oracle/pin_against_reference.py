@@ -103,6 +103,44 @@ def pin_controlnet(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'controlnet.safetensors'}")
 
 
+def pin_denoise_step(write: bool) -> None:
+    """One full denoising step of the reference's StableDiffusion_1 (LatentDiffusionModel.forward,
+    model.py:128-159: contexts, CFG doubling, sigma scaling, UNet, CFG combine, Euler update) on keyed
+    weights; own generator and fixture file."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.solvers import Euler
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.model import StableDiffusion_1
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+    from safetensors.torch import save_file
+
+    from oracle import euler as oeuler
+    from oracle import unet as ounet
+    from oracle.weights import keyed_state_dict
+
+    print("StableDiffusion_1 denoising step (CFG + Euler)")
+    gen = torch.Generator().manual_seed(777)
+    g = lambda *s: torch.randn(*s, generator=gen)
+    with torch.no_grad():
+        unet = SD1UNet(4)
+        shapes = {k: tuple(v.shape) for k, v in unet.state_dict().items()}
+        sdict = keyed_state_dict(shapes, seed=1)
+        unet.load_state_dict(sdict)
+        sd = StableDiffusion_1(unet=unet, solver=Euler(num_inference_steps=30))
+        x = g(2, 4, 32, 32) * float(sd.solver.init_noise_sigma)
+        ctx = g(4, 77, 768)  # unconditional block first, conditional second (model.py:137)
+        fx = {"step.x": x, "step.ctx": ctx}
+        schedule = oeuler.EulerSchedule(30)
+        for step, scale in ((0, 7.5), (7, 5.0), (29, 7.5)):
+            y = sd(x, step=step, clip_text_embedding=ctx, condition_scale=scale)
+            fx[f"step.y_{step}"] = y
+            mine = oeuler.denoise_step(lambda lat, ts: ounet.sd1_unet(sdict, lat, ts, ctx), schedule, x, step, scale)
+            _close(f"denoise step {step} (scale {scale})", mine, y)
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "step.safetensors"))
+        print(f"  wrote {GOLDEN / 'step.safetensors'}")
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -334,6 +372,9 @@ def main(write: bool) -> None:
 if __name__ == "__main__":
     if "--only-controlnet" in sys.argv:
         pin_controlnet(write="--check" not in sys.argv)
+    elif "--only-step" in sys.argv:
+        pin_denoise_step(write="--check" not in sys.argv)
     else:
         main(write="--check" not in sys.argv)
         pin_controlnet(write="--check" not in sys.argv)
+        pin_denoise_step(write="--check" not in sys.argv)

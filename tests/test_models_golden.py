@@ -184,6 +184,20 @@ def test_sdxl_control_lora_host():
     check(run_control_lora(unet, adapter, f, "cpu", torch.float32), f["cl.y"], "host")
 
 
+def test_sd1_denoising_step_host():
+    """LatentDiffusionModel.forward (model.py:128-159 in the reference): contexts, CFG doubling, sigma
+    scaling, UNet, CFG combine, Euler update - one whole step of StableDiffusion_1 against the
+    reference's recorded outputs at the first, a middle and the last step."""
+    from refiners_b200.foundationals.latent_diffusion import StableDiffusion_1
+
+    f = load_file(str(GOLDEN / "step.safetensors"))
+    sd = StableDiffusion_1(unet=load_unet(SD1UNet, seed=1), solver=Euler(num_inference_steps=30))
+    for step, scale in ((0, 7.5), (7, 5.0), (29, 7.5)):
+        with no_grad():
+            y = sd(f["step.x"], step=step, clip_text_embedding=f["step.ctx"], condition_scale=scale)
+        check(y, f[f"step.y_{step}"], "host")
+
+
 def load_controlnet_unet(device="cpu", dtype=torch.float32):
     """SD1UNet + SD1ControlnetAdapter('canny', scale 0.9, decay 0.825) with keyed weights (seed 4) - the
     construction recorded by oracle/pin_against_reference.py::pin_controlnet."""

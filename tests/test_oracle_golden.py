@@ -104,6 +104,19 @@ def test_sd1_controlnet_full():
     close(ounet.sd1_unet(sd, f["cn.x"], f["cn.timestep"], f["cn.ctx"]), f["cn.y_plain"], rel=2e-5)
 
 
+def test_denoise_step_full():
+    """oracle.euler.denoise_step over the oracle SD1UNet against the reference's StableDiffusion_1 step."""
+    from oracle import euler as oeuler
+    from refiners_b200.foundationals.latent_diffusion import SD1UNet
+
+    f = load_file(str(GOLDEN / "step.safetensors"))
+    shapes = {k: tuple(v.shape) for k, v in SD1UNet(4, device="meta").state_dict().items()}
+    sd = keyed_state_dict(shapes, seed=1)
+    schedule = oeuler.EulerSchedule(30)
+    unet = lambda lat, ts: ounet.sd1_unet(sd, lat, ts, f["step.ctx"])
+    close(oeuler.denoise_step(unet, schedule, f["step.x"], 7, 5.0), f["step.y_7"], rel=2e-5)
+
+
 def test_fast_mode_matches_golden():
     """oracle.ops.FAST (the fused ATen CPU calls the reference itself makes; used only for the timed
     CPU baseline) is pinned to the same golden vectors."""
