@@ -203,11 +203,12 @@ def dominant_kernel_roofline(device: torch.device, peaks: dict, peaks_kind: str)
     achieved = flops / (ms * 1e-3) / 1e12
     peak = float(peaks["bf16_tflops"])
     return {
-        "bound": "tensor", "kernel": "tc_gemm_kernel<bf16,256> [16384x1280]x[1280x1280]^T", "achieved": achieved,
+        "bound": "tensor", "kernel": "tc_gemm_kernel<bf16,256,cta_group::2 pair> [16384x1280]x[1280x1280]^T", "achieved": achieved,
         "peak": peak, "peak_source": f"{peaks_kind} bf16_tflops (burst: kernel timed alone)", "unit": "TFLOP/s",
         "frac": achieved / peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this shape, one `ncu --set full` launch
-        # (profiles/r01_ncu_full_gemm_full.txt); algorithmic bytes are 87.2 MB, the output mostly stays in L2
+        # (profiles/r01_ncu_full_gemm_full.txt, captured in the multicast-pair mode: DRAM traffic is the compulsory
+        # operand read either way); algorithmic bytes are 87.2 MB, the output mostly stays in L2
         "traffic": 47.49e6, "traffic_source": "profiles/r01_ncu_full_gemm_full.txt", "ms_per_launch": ms,
         "algorithmic_flops_per_launch": flops,
     }
