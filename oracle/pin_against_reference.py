@@ -141,6 +141,35 @@ def pin_denoise_step(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'step.safetensors'}")
 
 
+def pin_vae(write: bool) -> None:
+    """LatentDiffusionAutoencoder.encode / decode (auto_encoder.py:305-331) on keyed weights; own fixture file."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+    from safetensors.torch import save_file
+
+    from oracle import vae as ovae
+    from oracle.weights import keyed_state_dict
+
+    print("LatentDiffusionAutoencoder")
+    gen = torch.Generator().manual_seed(2468)
+    with torch.no_grad():
+        lda = LatentDiffusionAutoencoder()
+        shapes = {k: tuple(v.shape) for k, v in lda.state_dict().items()}
+        sdict = keyed_state_dict(shapes, seed=5)
+        lda.load_state_dict(sdict)
+        z = torch.randn(2, 4, 12, 16, generator=gen)
+        image = torch.rand(1, 3, 72, 56, generator=gen) * 2 - 1
+        x = lda.decode(z)
+        lat = lda.encode(image)
+        _close("VAE decode", ovae.decode(sdict, z), x)
+        _close("VAE encode", ovae.encode(sdict, image), lat)
+    fx = {"vae.z": z, "vae.decoded": x, "vae.image": image, "vae.encoded": lat}
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "vae.safetensors"))
+        print(f"  wrote {GOLDEN / 'vae.safetensors'}")
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -372,9 +401,13 @@ def main(write: bool) -> None:
 if __name__ == "__main__":
     if "--only-controlnet" in sys.argv:
         pin_controlnet(write="--check" not in sys.argv)
+    elif "--only-vae" in sys.argv:
+        pin_vae(write="--check" not in sys.argv)
     elif "--only-step" in sys.argv:
         pin_denoise_step(write="--check" not in sys.argv)
+        pin_vae(write="--check" not in sys.argv)
     else:
         main(write="--check" not in sys.argv)
         pin_controlnet(write="--check" not in sys.argv)
         pin_denoise_step(write="--check" not in sys.argv)
+        pin_vae(write="--check" not in sys.argv)

@@ -76,3 +76,43 @@ def load_tensors(path: Path | str, /, device: torch.device | str = "cpu") -> dic
     if str(path).endswith(".safetensors"):
         return load_from_safetensors(path, device=device)
     return torch.load(path, map_location=device, weights_only=True)
+
+
+# ---------------------------------------------------------------------------- PIL <-> tensors
+# (utils.py:116-200 in the reference: values in [0, 1], batch axis first, channels by PIL mode)
+def image_to_tensor(image: Any, device: torch.device | str | None = None, dtype: torch.dtype | None = None) -> Tensor:
+    """PIL image -> ``[1, C, H, W]`` in [0, 1]; C = 1 (mode L), 3 (RGB) or 4 (RGBA)."""
+    import numpy as np
+
+    pixels = torch.tensor(np.array(image).astype(np.float32) / 255.0, device=device, dtype=dtype)
+    if image.mode == "L":
+        pixels = pixels.unsqueeze(0)
+    elif image.mode in ("RGB", "RGBA"):
+        pixels = pixels.permute(2, 0, 1)
+    else:
+        raise ValueError(f"Unsupported image mode: {image.mode}")
+    return pixels.unsqueeze(0)
+
+
+def images_to_tensor(images: list[Any], device: torch.device | str | None = None, dtype: torch.dtype | None = None) -> Tensor:
+    return torch.cat([image_to_tensor(image, device=device, dtype=dtype) for image in images])
+
+
+def tensor_to_image(tensor: Tensor) -> Any:
+    """``[1, C, H, W]`` (clamped to [0, 1]) -> PIL image of mode L / RGB / RGBA."""
+    from PIL import Image
+
+    assert tensor.ndim == 4 and tensor.shape[0] == 1, f"Unsupported tensor shape: {tensor.shape}"
+    channels = tensor.shape[1]
+    data = tensor.clamp(0, 1).squeeze(0).to(torch.float32)  # numpy has no bfloat16
+    if channels == 1:
+        data = data.squeeze(0)
+    elif channels in (3, 4):
+        data = data.permute(1, 2, 0)
+    else:
+        raise ValueError(f"Unsupported number of channels: {channels}")
+    return Image.fromarray((data.cpu().numpy() * 255).astype("uint8"))
+
+
+def tensor_to_images(tensor: Tensor) -> list[Any]:
+    return [tensor_to_image(t) for t in tensor.split(1)]

@@ -1,3 +1,4 @@
+from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
 from refiners_b200.foundationals.latent_diffusion.cross_attention import CrossAttentionBlock, CrossAttentionBlock2d
 from refiners_b200.foundationals.latent_diffusion.model import LatentDiffusionModel
 from refiners_b200.foundationals.latent_diffusion.range_adapter import RangeAdapter2d, RangeEncoder
@@ -13,5 +14,5 @@ from refiners_b200.foundationals.latent_diffusion.unet_blocks import (
 __all__ = [
     "CrossAttentionBlock", "CrossAttentionBlock2d", "LatentDiffusionModel", "RangeAdapter2d", "RangeEncoder",
     "DDIM", "Euler", "Solver", "SolverParams", "SD1UNet", "StableDiffusion_1", "SDXLUNet", "StableDiffusion_XL",
-    "ResidualAccumulator", "ResidualBlock", "ResidualConcatenator",
+    "ResidualAccumulator", "ResidualBlock", "ResidualConcatenator", "LatentDiffusionAutoencoder",
 ]

@@ -198,6 +198,26 @@ def test_sd1_denoising_step_host():
         check(y, f[f"step.y_{step}"], "host")
 
 
+def test_vae_host():
+    """LatentDiffusionAutoencoder: encode / decode on keyed weights against the reference,
+    and the PIL round trip of the helpers."""
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+
+    f = load_file(str(GOLDEN / "vae.safetensors"))
+    lda = LatentDiffusionAutoencoder(device="meta")
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in lda.state_dict().items()}, seed=5)
+    lda.load_state_dict(sd, assign=True)
+    with no_grad():
+        check(lda.decode(f["vae.z"]), f["vae.decoded"], "host")
+        check(lda.encode(f["vae.image"]), f["vae.encoded"], "host")
+        images = lda.latents_to_images(f["vae.z"])
+    assert len(images) == 2 and images[0].size == (128, 96) and images[0].mode == "RGB"
+    want = ((f["vae.decoded"][:1] + 1) / 2).clamp(0, 1)
+    from refiners_b200.fluxion.utils import image_to_tensor
+
+    assert (image_to_tensor(images[0]) - want).abs().max().item() <= 1 / 255 + 1e-6
+
+
 def load_controlnet_unet(device="cpu", dtype=torch.float32):
     """SD1UNet + SD1ControlnetAdapter('canny', scale 0.9, decay 0.825) with keyed weights (seed 4) - the
     construction recorded by oracle/pin_against_reference.py::pin_controlnet."""

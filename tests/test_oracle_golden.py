@@ -117,6 +117,18 @@ def test_denoise_step_full():
     close(oeuler.denoise_step(unet, schedule, f["step.x"], 7, 5.0), f["step.y_7"], rel=2e-5)
 
 
+def test_vae_full():
+    """Oracle VAE (encode 72x56 image, decode 12x16 latents) against the reference's recorded outputs."""
+    from oracle import vae as ovae
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+
+    f = load_file(str(GOLDEN / "vae.safetensors"))
+    shapes = {k: tuple(v.shape) for k, v in LatentDiffusionAutoencoder(device="meta").state_dict().items()}
+    sd = keyed_state_dict(shapes, seed=5)
+    close(ovae.decode(sd, f["vae.z"]), f["vae.decoded"], rel=2e-5)
+    close(ovae.encode(sd, f["vae.image"]), f["vae.encoded"], rel=2e-5)
+
+
 def test_fast_mode_matches_golden():
     """oracle.ops.FAST (the fused ATen CPU calls the reference itself makes; used only for the timed
     CPU baseline) is pinned to the same golden vectors."""

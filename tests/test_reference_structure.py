@@ -107,6 +107,14 @@ def test_sam_vit_h(ref):
     same(SAMViTH(device="meta"), RViT(device="meta"))
 
 
+def test_vae(ref):
+    from refiners.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder as RVAE
+
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+
+    same(LatentDiffusionAutoencoder(device="meta"), RVAE(device="meta"))
+
+
 def test_solver_tables(ref):
     from refiners.foundationals.latent_diffusion.solvers import DDIM as RDDIM, Euler as REuler
 
