@@ -170,6 +170,44 @@ def pin_vae(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'vae.safetensors'}")
 
 
+def pin_dinov2(write: bool) -> None:
+    """DINOv2 ViT (dinov2/vit.py:289-413): the published small model at 224x224, and a tiny register + SwiGLU
+    configuration on a non-square input that exercises the antialiased bicubic resize of the positions."""
+    _import_reference()
+    import refiners.fluxion.layers as rfl
+    from refiners.foundationals.dinov2 import DINOv2_small, ViT
+    from safetensors.torch import save_file
+
+    from oracle import dinov2 as odino
+    from oracle.weights import keyed_state_dict
+
+    print("DINOv2 ViT")
+    gen = torch.Generator().manual_seed(1357)
+    fx = {}
+    with torch.no_grad():
+        small = DINOv2_small()
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in small.state_dict().items()}, seed=6)
+        small.load_state_dict(sd)
+        x = torch.randn(2, 3, 224, 224, generator=gen)
+        y = small(x)
+        _close("DINOv2_small", odino.vit(sd, x, patch_size=14, num_layers=12, num_heads=6), y)
+        fx.update({"small.x": x, "small.y": y})
+        tiny_cfg = dict(embedding_dim=64, patch_size=4, image_size=16, num_layers=2, num_heads=2, num_registers=3,
+                        feedforward_dim=96, interpolate_antialias=True)
+        tiny = ViT(activation=rfl.GLU(rfl.SiLU()), **tiny_cfg)
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in tiny.state_dict().items()}, seed=7)
+        tiny.load_state_dict(sd)
+        x = torch.randn(3, 3, 24, 20, generator=gen)
+        y = tiny(x)
+        _close("ViT tiny (registers, SwiGLU, 6x5 grid)", odino.vit(sd, x, patch_size=4, num_layers=2, num_heads=2, num_registers=3,
+                                                                    swiglu=True, interpolate_antialias=True), y)
+        fx.update({"tiny.x": x, "tiny.y": y})
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "dinov2.safetensors"))
+        print(f"  wrote {GOLDEN / 'dinov2.safetensors'}")
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -399,15 +437,15 @@ def main(write: bool) -> None:
 
 
 if __name__ == "__main__":
-    if "--only-controlnet" in sys.argv:
-        pin_controlnet(write="--check" not in sys.argv)
-    elif "--only-vae" in sys.argv:
-        pin_vae(write="--check" not in sys.argv)
-    elif "--only-step" in sys.argv:
-        pin_denoise_step(write="--check" not in sys.argv)
-        pin_vae(write="--check" not in sys.argv)
-    else:
-        main(write="--check" not in sys.argv)
-        pin_controlnet(write="--check" not in sys.argv)
-        pin_denoise_step(write="--check" not in sys.argv)
-        pin_vae(write="--check" not in sys.argv)
+    write = "--check" not in sys.argv
+    sections = {
+        "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-dinov2": pin_dinov2,
+    }
+    chosen = [fn for flag, fn in sections.items() if flag in sys.argv]
+    if chosen:
+        for fn in chosen:
+            fn(write)
+    else:  # everything: the main fixture files first (one shared random stream), then the self-seeded sections
+        main(write)
+        for fn in sections.values():
+            fn(write)

@@ -218,6 +218,25 @@ def test_vae_host():
     assert (image_to_tensor(images[0]) - want).abs().max().item() <= 1 / 255 + 1e-6
 
 
+def test_dinov2_host():
+    """DINOv2 ViT on keyed weights against the reference: the published small model and a tiny
+    registers + SwiGLU configuration whose input grid (6 x 5) differs from the positional grid (4 x 4)."""
+    from refiners_b200.foundationals.dinov2 import DINOv2_small, ViT
+
+    f = load_file(str(GOLDEN / "dinov2.safetensors"))
+
+    def keyed(model, seed):
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=seed)
+        model.load_state_dict(sd, assign=True)
+        return model
+
+    with no_grad():
+        check(keyed(DINOv2_small(device="meta"), 6)(f["small.x"]), f["small.y"], "host")
+        tiny = ViT(embedding_dim=64, patch_size=4, image_size=16, num_layers=2, num_heads=2, num_registers=3, feedforward_dim=96,
+                   interpolate_antialias=True, activation=fl.GLU(fl.SiLU()), device="meta")
+        check(keyed(tiny, 7)(f["tiny.x"]), f["tiny.y"], "host")
+
+
 def load_controlnet_unet(device="cpu", dtype=torch.float32):
     """SD1UNet + SD1ControlnetAdapter('canny', scale 0.9, decay 0.825) with keyed weights (seed 4) - the
     construction recorded by oracle/pin_against_reference.py::pin_controlnet."""

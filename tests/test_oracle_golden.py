@@ -129,6 +129,16 @@ def test_vae_full():
     close(ovae.encode(sd, f["vae.image"]), f["vae.encoded"], rel=2e-5)
 
 
+def test_dinov2_full():
+    """Oracle ViT against the reference: DINOv2_small at 224x224 and a tiny registers + SwiGLU model on 24x20."""
+    from oracle import dinov2 as odino
+    from refiners_b200.foundationals.dinov2 import DINOv2_small
+
+    f = load_file(str(GOLDEN / "dinov2.safetensors"))
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in DINOv2_small(device="meta").state_dict().items()}, seed=6)
+    close(odino.vit(sd, f["small.x"], patch_size=14, num_layers=12, num_heads=6), f["small.y"], rel=2e-5)
+
+
 def test_fast_mode_matches_golden():
     """oracle.ops.FAST (the fused ATen CPU calls the reference itself makes; used only for the timed
     CPU baseline) is pinned to the same golden vectors."""

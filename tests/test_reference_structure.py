@@ -115,6 +115,15 @@ def test_vae(ref):
     same(LatentDiffusionAutoencoder(device="meta"), RVAE(device="meta"))
 
 
+@pytest.mark.parametrize("name", ["DINOv2_small", "DINOv2_base_reg", "DINOv2_large", "DINOv2_giant_reg"])
+def test_dinov2(ref, name):
+    import refiners.foundationals.dinov2 as theirs
+
+    import refiners_b200.foundationals.dinov2 as mine
+
+    same(getattr(mine, name)(device="meta"), getattr(theirs, name)(device="meta"))
+
+
 def test_solver_tables(ref):
     from refiners.foundationals.latent_diffusion.solvers import DDIM as RDDIM, Euler as REuler
 
