@@ -4,9 +4,9 @@ Per-step behaviour follows /root/reference/src/refiners/foundationals/latent_dif
 `ImageProjection` :24-45, `ImageCrossAttention` :237-278, `CrossAttentionAdapter` :281-347,
 `IPAdapter` :350-455, and stable_diffusion_xl/image_prompt.py:9-65 (`SDXLIPAdapter`).
 
-Scope: the CLIP image encoder and the fine-grained PerceiverResampler run once per prompt, outside
-the denoising loop - they are optional constructor arguments here and
-the benchmarks feed a synthetic ``clip_image_embedding`` through ``set_clip_image_embedding``.
+Scope: the CLIP image encoder runs once per prompt, outside the denoising loop - it
+is an optional constructor argument here and the benchmarks feed a synthetic ``clip_image_embedding`` through
+``set_clip_image_embedding``.  The fine-grained image projection (`PerceiverResampler`, perceiver.py) is built.
 
 B200 addition: after injection each cross-attention contains ``Sum(SDPA, ImageCrossAttention)``;
 on CUDA that Sum runs as ONE flash-attention launch with two key/value sets and two independent
@@ -27,6 +27,7 @@ from refiners_b200.engine import fusion
 from refiners_b200.fluxion.adapters.adapter import Adapter
 from refiners_b200.fluxion.layers.leaves import ScaledDotProductAttention
 from refiners_b200.foundationals.latent_diffusion.cross_attention import CrossAttentionBlock2d
+from refiners_b200.foundationals.latent_diffusion.perceiver import PerceiverResampler
 
 T = TypeVar("T", bound=fl.Chain)
 TIPAdapter = TypeVar("TIPAdapter", bound="IPAdapter[Any]")
@@ -225,14 +226,24 @@ class SDXLIPAdapter(IPAdapter[fl.Chain]):
         weights: dict[str, Tensor] | None = None,
         clip_image_embedding_dim: int = 1024,
     ) -> None:
-        if image_proj is None and not fine_grained:
+        if image_proj is None:
             xattn = target.ensure_find(CrossAttentionBlock2d)
-            image_proj = ImageProjection(
-                clip_image_embedding_dim=clip_image_embedding_dim,
-                clip_text_embedding_dim=xattn.context_embedding_dim,
-                device=target.device,
-                dtype=target.dtype,
-            )
+            if fine_grained:
+                # IP-Adapter "plus": 16 tokens resampled from the CLIP-H patch features (1280 wide before the
+                # final projection); the latent width stays 1280 whatever the text width (sdxl/image_prompt.py:43-53)
+                image_proj = PerceiverResampler(
+                    latents_dim=1280, num_attention_layers=4, num_attention_heads=20, head_dim=64, num_tokens=16,
+                    input_dim=1280, output_dim=xattn.context_embedding_dim, device=target.device, dtype=target.dtype,
+                )
+            else:
+                image_proj = ImageProjection(
+                    clip_image_embedding_dim=clip_image_embedding_dim,
+                    clip_text_embedding_dim=xattn.context_embedding_dim,
+                    device=target.device,
+                    dtype=target.dtype,
+                )
+        elif fine_grained:
+            assert isinstance(image_proj, PerceiverResampler)
         super().__init__(
             target=target,
             clip_image_encoder=clip_image_encoder,

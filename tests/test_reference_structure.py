@@ -78,6 +78,28 @@ def test_sdxl_unet_control_lora_and_ip_adapter(ref):
     same(mine, theirs)
 
 
+def test_ip_adapter_plus_perceiver_resampler(ref):
+    """fine_grained=True: the 16-token PerceiverResampler image projection, structure and numbers (same weights)."""
+    from refiners.foundationals.latent_diffusion.image_prompt import PerceiverResampler as RResampler
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.image_prompt import SDXLIPAdapter as RIP
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.unet import SDXLUNet as RUNet
+
+    from refiners_b200.foundationals.latent_diffusion import SDXLUNet
+    from refiners_b200.foundationals.latent_diffusion.image_prompt import SDXLIPAdapter
+    from refiners_b200.foundationals.latent_diffusion.perceiver import PerceiverResampler
+
+    ia, ib = SDXLIPAdapter(SDXLUNet(4, device="meta"), fine_grained=True), RIP(RUNet(4, device="meta"), fine_grained=True)
+    assert isinstance(ia.image_proj, PerceiverResampler)
+    same(ia.image_proj, ib.image_proj)
+    cfg = dict(latents_dim=64, num_attention_layers=2, num_attention_heads=4, head_dim=16, num_tokens=5, input_dim=48, output_dim=40)
+    torch.manual_seed(0)
+    mine, theirs = PerceiverResampler(**cfg), RResampler(**cfg)
+    mine.load_state_dict(theirs.state_dict())
+    x = torch.randn(3, 11, 48)
+    with torch.no_grad():
+        assert torch.equal(mine(x), theirs(x))
+
+
 def test_lora_adapters_on_cross_attention(ref):
     import refiners.fluxion.layers as rfl
     from refiners.fluxion.adapters.lora import LinearLora as RLora, LoraAdapter as RAdapter
