@@ -28,18 +28,10 @@ class PatchEncoder(fl.Chain):
     """Non-overlapping patch embedding: conv(k = stride = patch) then NCHW -> NHWC."""
 
     def __init__(
-        self,
-        in_channels: int,
-        out_channels: int,
-        patch_size: int = 16,
-        use_bias: bool = True,
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, in_channels: int, out_channels: int, patch_size: int = 16, use_bias: bool = True,
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.patch_size = patch_size
-        self.use_bias = use_bias
+        self.in_channels, self.out_channels, self.patch_size, self.use_bias = in_channels, out_channels, patch_size, use_bias
         super().__init__(
             fl.Conv2d(
                 in_channels,
@@ -56,14 +48,10 @@ class PatchEncoder(fl.Chain):
 
 class PositionalEncoder(fl.Residual):
     def __init__(
-        self,
-        embedding_dim: int,
-        image_embedding_size: tuple[int, int],
-        device: Device | str | None = None,
+        self, embedding_dim: int, image_embedding_size: tuple[int, int], device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim = embedding_dim
-        self.image_embedding_size = image_embedding_size
+        self.embedding_dim, self.image_embedding_size = embedding_dim, image_embedding_size
         super().__init__(
             fl.Parameter(image_embedding_size[0], image_embedding_size[1], embedding_dim, device=device, dtype=dtype)
         )
@@ -74,16 +62,11 @@ class RelativePositionAttention(fl.WeightedModule):
     position terms: logits = q k^T d^-1/2 + q . R_v[h - kh] + q . R_h[w - kw]."""
 
     def __init__(
-        self,
-        embedding_dim: int,
-        num_heads: int,
-        spatial_size: tuple[int, int],
-        device: Device | str | None = None,
+        self, embedding_dim: int, num_heads: int, spatial_size: tuple[int, int], device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
         super().__init__()
-        self.embedding_dim = embedding_dim
-        self.num_heads = num_heads
+        self.embedding_dim, self.num_heads = embedding_dim, num_heads
         self.head_dim = embedding_dim // num_heads
         self.spatial_size = spatial_size
         self.horizontal_embedding = nn.Parameter(torch.zeros(2 * spatial_size[0] - 1, self.head_dim, device=device, dtype=dtype))
@@ -127,22 +110,14 @@ class RelativePositionAttention(fl.WeightedModule):
 
 class FusedSelfAttention(fl.Chain):
     def __init__(
-        self,
-        embedding_dim: int = 768,
-        spatial_size: tuple[int, int] = (64, 64),
-        num_heads: int = 1,
-        use_bias: bool = True,
-        is_causal: bool = False,
-        device: Device | str | None = None,
+        self, embedding_dim: int = 768, spatial_size: tuple[int, int] = (64, 64), num_heads: int = 1,
+        use_bias: bool = True, is_causal: bool = False, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
         assert embedding_dim % num_heads == 0, (
             f"Embedding dim (embedding_dim={embedding_dim}) must be divisible by num heads (num_heads={num_heads})"
         )
-        self.embedding_dim = embedding_dim
-        self.num_heads = num_heads
-        self.use_bias = use_bias
-        self.is_causal = is_causal
+        self.embedding_dim, self.num_heads, self.use_bias, self.is_causal = embedding_dim, num_heads, use_bias, is_causal
         super().__init__(
             fl.Linear(embedding_dim, 3 * embedding_dim, bias=use_bias, device=device, dtype=dtype),
             RelativePositionAttention(embedding_dim, num_heads, spatial_size, device=device, dtype=dtype),
@@ -152,14 +127,10 @@ class FusedSelfAttention(fl.Chain):
 
 class FeedForward(fl.Chain):
     def __init__(
-        self,
-        embedding_dim: int,
-        feedforward_dim: int,
-        device: Device | str | None = None,
+        self, embedding_dim: int, feedforward_dim: int, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim = embedding_dim
-        self.feedforward_dim = feedforward_dim
+        self.embedding_dim, self.feedforward_dim = embedding_dim, feedforward_dim
         super().__init__(
             fl.Linear(embedding_dim, feedforward_dim, bias=True, device=device, dtype=dtype),
             fl.GeLU(),
@@ -208,22 +179,12 @@ class WindowMerge(fl.ContextModule):
 
 class TransformerLayer(fl.Chain):
     def __init__(
-        self,
-        embedding_dim: int,
-        num_heads: int,
-        feedforward_dim: int,
-        image_embedding_size: tuple[int, int],
-        window_size: int | None = None,
-        layer_norm_eps: float = 1e-6,
-        device: Device | str | None = None,
+        self, embedding_dim: int, num_heads: int, feedforward_dim: int, image_embedding_size: tuple[int, int],
+        window_size: int | None = None, layer_norm_eps: float = 1e-6, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim = embedding_dim
-        self.num_heads = num_heads
-        self.feedforward_dim = feedforward_dim
-        self.window_size = window_size
-        self.layer_norm_eps = layer_norm_eps
-        self.image_embedding_size = image_embedding_size
+        self.embedding_dim, self.num_heads, self.feedforward_dim, self.window_size = embedding_dim, num_heads, feedforward_dim, window_size
+        self.layer_norm_eps, self.image_embedding_size = layer_norm_eps, image_embedding_size
         windowed = window_size is not None
         spatial = (window_size, window_size) if windowed else image_embedding_size
         kw = dict(device=device, dtype=dtype)
@@ -265,20 +226,13 @@ class SAMViT(fl.Chain):
     """[B, 3, 1024, 1024] image -> [B, 256, 64, 64] embedding."""
 
     def __init__(
-        self,
-        embedding_dim: int,
-        num_layers: int,
-        num_heads: int,
-        global_attention_indices: tuple[int, ...] | None = None,
-        device: Device | str | None = None,
+        self, embedding_dim: int, num_layers: int, num_heads: int,
+        global_attention_indices: tuple[int, ...] | None = None, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim = embedding_dim
-        self.num_layers = num_layers
-        self.num_heads = num_heads
+        self.embedding_dim, self.num_layers, self.num_heads = embedding_dim, num_layers, num_heads
         self.image_size = (1024, 1024)
-        self.patch_size = 16
-        self.window_size = 14
+        self.patch_size, self.window_size = 16, 14
         self.image_embedding_size = (self.image_size[0] // self.patch_size, self.image_size[1] // self.patch_size)
         self.feed_forward_dim = 4 * self.embedding_dim
         self.global_attention_indices = global_attention_indices or tuple()
