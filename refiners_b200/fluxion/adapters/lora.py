@@ -30,17 +30,10 @@ DType = torch.dtype
 
 class Lora(Generic[T], fl.Chain, ABC):
     def __init__(
-        self,
-        name: str,
-        /,
-        rank: int = 16,
-        scale: float = 1.0,
-        device: Device | str | None = None,
+        self, name: str, /, rank: int = 16, scale: float = 1.0, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.name = name
-        self._rank = rank
-        self._scale = scale
+        self.name, self._rank, self._scale = name, rank, scale
         down, up = self.lora_layers(device=device, dtype=dtype)
         super().__init__(down, up, fl.Multiply(scale))
         self.reset_parameters()
@@ -99,10 +92,7 @@ class Lora(Generic[T], fl.Chain, ABC):
         return loras
 
     def auto_attach(
-        self,
-        target: fl.Chain,
-        include: list[str] | None = None,
-        exclude: list[str] | None = None,
+        self, target: fl.Chain, include: list[str] | None = None, exclude: list[str] | None = None,
     ) -> "tuple[LoraAdapter, fl.Chain | None] | None":
         """Find the first compatible, not yet adapted layer of ``target``.  Returns the adapter
         to inject and the parent to inject it into (``None`` when this LoRA was appended to an
@@ -135,18 +125,10 @@ class Lora(Generic[T], fl.Chain, ABC):
 
 class LinearLora(Lora[fl.Linear]):
     def __init__(
-        self,
-        name: str,
-        /,
-        in_features: int,
-        out_features: int,
-        rank: int = 16,
-        scale: float = 1.0,
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, name: str, /, in_features: int, out_features: int, rank: int = 16, scale: float = 1.0,
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.in_features = in_features
-        self.out_features = out_features
+        self.in_features, self.out_features = in_features, out_features
         super().__init__(name, rank=rank, scale=scale, device=device, dtype=dtype)
 
     @classmethod
@@ -180,23 +162,11 @@ class LinearLora(Lora[fl.Linear]):
 
 class Conv2dLora(Lora[fl.Conv2d]):
     def __init__(
-        self,
-        name: str,
-        /,
-        in_channels: int,
-        out_channels: int,
-        rank: int = 16,
-        scale: float = 1.0,
-        kernel_size: tuple[int, int] = (1, 3),
-        stride: tuple[int, int] = (1, 1),
-        padding: tuple[int, int] = (0, 1),
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, name: str, /, in_channels: int, out_channels: int, rank: int = 16, scale: float = 1.0,
+        kernel_size: tuple[int, int] = (1, 3), stride: tuple[int, int] = (1, 1), padding: tuple[int, int] = (0, 1),
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.kernel_size = kernel_size
-        self.stride = stride
+        self.in_channels, self.out_channels, self.kernel_size, self.stride = in_channels, out_channels, kernel_size, stride
         self.padding = padding
         super().__init__(name, rank=rank, scale=scale, device=device, dtype=dtype)
 
@@ -335,12 +305,8 @@ class LoraAdapter(fl.Sum, Adapter[fl.WeightedModule]):
 
 
 def _auto_attach_loras(
-    loras: dict[str, Lora[Any]],
-    target: fl.Chain,
-    /,
-    include: list[str] | None = None,
-    exclude: list[str] | None = None,
-    debug_map: list[tuple[str, str]] | None = None,
+    loras: dict[str, Lora[Any]], target: fl.Chain, /, include: list[str] | None = None,
+    exclude: list[str] | None = None, debug_map: list[tuple[str, str]] | None = None,
 ) -> list[str]:
     failed: list[str] = []
     for key, lora in loras.items():
@@ -360,13 +326,8 @@ def _auto_attach_loras(
 
 
 def auto_attach_loras(
-    loras: dict[str, Lora[Any]],
-    target: fl.Chain,
-    /,
-    include: list[str] | None = None,
-    exclude: list[str] | None = None,
-    sanity_check: bool = True,
-    debug_map: list[tuple[str, str]] | None = None,
+    loras: dict[str, Lora[Any]], target: fl.Chain, /, include: list[str] | None = None,
+    exclude: list[str] | None = None, sanity_check: bool = True, debug_map: list[tuple[str, str]] | None = None,
 ) -> list[str]:
     """Attach each LoRA to the first compatible layer of ``target``; returns the keys that
     found no home.  With ``sanity_check`` a second pass with copies must attach nothing."""

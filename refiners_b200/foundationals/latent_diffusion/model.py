@@ -24,14 +24,8 @@ DType = torch.dtype
 
 class LatentDiffusionModel(fl.Module, ABC):
     def __init__(
-        self,
-        unet: fl.Chain,
-        lda: fl.Chain | None,
-        clip_text_encoder: fl.Chain | None,
-        solver: Solver,
-        classifier_free_guidance: bool = True,
-        device: Device | str = "cpu",
-        dtype: DType = torch.float32,
+        self, unet: fl.Chain, lda: fl.Chain | None, clip_text_encoder: fl.Chain | None, solver: Solver,
+        classifier_free_guidance: bool = True, device: Device | str = "cpu", dtype: DType = torch.float32,
     ) -> None:
         super().__init__()
         self.device: Device = device if isinstance(device, Device) else Device(device)
@@ -67,9 +61,7 @@ class LatentDiffusionModel(fl.Module, ABC):
 
     @staticmethod
     def sample_noise(
-        size: tuple[int, ...],
-        device: Device | None = None,
-        dtype: DType | None = None,
+        size: tuple[int, ...], device: Device | None = None, dtype: DType | None = None,
         offset_noise: float | None = None,
     ) -> Tensor:
         noise = torch.randn(size=size, device=device, dtype=dtype)
@@ -102,12 +94,12 @@ class LatentDiffusionModel(fl.Module, ABC):
         return False
 
     def compute_self_attention_guidance(
-        self, x: Tensor, noise: Tensor, step: int, *, clip_text_embedding: Tensor, **kwargs: Tensor
+        self, x: Tensor, noise: Tensor, step: int, *, clip_text_embedding: Tensor, **kwargs: Tensor,
     ) -> Tensor:
         raise NotImplementedError("self-attention guidance is out of the hot-path scope (SURVEY.md section 2 #18)")
 
     def forward(
-        self, x: Tensor, step: int, *, clip_text_embedding: Tensor, condition_scale: float = 7.5, **kwargs: Tensor
+        self, x: Tensor, step: int, *, clip_text_embedding: Tensor, condition_scale: float = 7.5, **kwargs: Tensor,
     ) -> Tensor:
         cfg = self.classifier_free_guidance
         if cfg:

@@ -36,14 +36,10 @@ def compute_sinusoidal_embedding(x: Tensor, embedding_dim: int) -> Tensor:
 
 class RangeEncoder(fl.Chain):
     def __init__(
-        self,
-        sinusoidal_embedding_dim: int,
-        embedding_dim: int,
-        device: Device | str | None = None,
+        self, sinusoidal_embedding_dim: int, embedding_dim: int, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.sinusoidal_embedding_dim = sinusoidal_embedding_dim
-        self.embedding_dim = embedding_dim
+        self.sinusoidal_embedding_dim, self.embedding_dim = sinusoidal_embedding_dim, embedding_dim
         super().__init__(
             fl.Lambda(self.compute_sinusoidal_embedding),
             fl.Converter(set_device=False, set_dtype=True),
@@ -58,16 +54,10 @@ class RangeEncoder(fl.Chain):
 
 class RangeAdapter2d(fl.Sum, Adapter[fl.Conv2d]):
     def __init__(
-        self,
-        target: fl.Conv2d,
-        channels: int,
-        embedding_dim: int,
-        context_key: str,
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, target: fl.Conv2d, channels: int, embedding_dim: int, context_key: str,
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.channels = channels
-        self.embedding_dim = embedding_dim
+        self.channels, self.embedding_dim = channels, embedding_dim
         with self.setup_adapter(target):
             super().__init__(
                 target,

@@ -27,12 +27,8 @@ class DDIM(Solver):
     )
 
     def __init__(
-        self,
-        num_inference_steps: int,
-        first_inference_step: int = 0,
-        params: BaseSolverParams | None = None,
-        device: torch.device | str = "cpu",
-        dtype: torch.dtype = torch.float32,
+        self, num_inference_steps: int, first_inference_step: int = 0, params: BaseSolverParams | None = None,
+        device: torch.device | str = "cpu", dtype: torch.dtype = torch.float32,
     ) -> None:
         if params and params.model_prediction_type not in (ModelPredictionType.NOISE, None):
             raise NotImplementedError

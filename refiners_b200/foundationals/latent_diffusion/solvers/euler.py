@@ -19,12 +19,8 @@ from refiners_b200.foundationals.latent_diffusion.solvers.solver import (
 
 class Euler(Solver):
     def __init__(
-        self,
-        num_inference_steps: int,
-        first_inference_step: int = 0,
-        params: BaseSolverParams | None = None,
-        device: torch.device | str = "cpu",
-        dtype: torch.dtype = torch.float32,
+        self, num_inference_steps: int, first_inference_step: int = 0, params: BaseSolverParams | None = None,
+        device: torch.device | str = "cpu", dtype: torch.dtype = torch.float32,
     ) -> None:
         if params and params.noise_schedule not in (NoiseSchedule.QUADRATIC, None):
             raise NotImplementedError

@@ -103,16 +103,11 @@ class Solver(fl.Module, ABC):
     )
 
     def __init__(
-        self,
-        num_inference_steps: int,
-        first_inference_step: int = 0,
-        params: BaseSolverParams | None = None,
-        device: Device | str = "cpu",
-        dtype: DType = torch.float32,
+        self, num_inference_steps: int, first_inference_step: int = 0, params: BaseSolverParams | None = None,
+        device: Device | str = "cpu", dtype: DType = torch.float32,
     ) -> None:
         super().__init__()
-        self.num_inference_steps = num_inference_steps
-        self.first_inference_step = first_inference_step
+        self.num_inference_steps, self.first_inference_step = num_inference_steps, first_inference_step
         self.params = self.resolve_params(params)
         self.scale_factors = self.sample_noise_schedule()
         alphas_cumprod = self.scale_factors.cumprod(dim=0)
@@ -133,10 +128,7 @@ class Solver(fl.Module, ABC):
 
     @staticmethod
     def generate_timesteps(
-        spacing: TimestepSpacing,
-        num_inference_steps: int,
-        num_train_timesteps: int = 1000,
-        offset: int = 0,
+        spacing: TimestepSpacing, num_inference_steps: int, num_train_timesteps: int = 1000, offset: int = 0,
     ) -> Tensor:
         top = num_train_timesteps - 1 + offset
         if spacing is TimestepSpacing.LINSPACE:

@@ -19,13 +19,8 @@ class StableDiffusion_XL(LatentDiffusionModel):
     unet: SDXLUNet
 
     def __init__(
-        self,
-        unet: SDXLUNet | None = None,
-        lda: fl.Chain | None = None,
-        clip_text_encoder: fl.Chain | None = None,
-        solver: Solver | None = None,
-        device: torch.device | str = "cpu",
-        dtype: torch.dtype = torch.float32,
+        self, unet: SDXLUNet | None = None, lda: fl.Chain | None = None, clip_text_encoder: fl.Chain | None = None,
+        solver: Solver | None = None, device: torch.device | str = "cpu", dtype: torch.dtype = torch.float32,
     ) -> None:
         super().__init__(
             unet=unet or SDXLUNet(in_channels=4),

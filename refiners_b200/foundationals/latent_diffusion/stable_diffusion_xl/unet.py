@@ -37,9 +37,7 @@ class TextTimeEmbedding(fl.Chain):
     """cat(pooled text embedding, sinusoid(time_ids)) -> 2-layer MLP -> [B, 1280]."""
 
     def __init__(self, device: Device | str | None = None, dtype: DType | None = None) -> None:
-        self.timestep_embedding_dim = 1280
-        self.time_ids_embedding_dim = 256
-        self.text_time_embedding_dim = 2816
+        self.timestep_embedding_dim, self.time_ids_embedding_dim, self.text_time_embedding_dim = 1280, 256, 2816
         super().__init__(
             fl.Concatenate(
                 fl.UseContext(context="diffusion", key="pooled_text_embedding"),
@@ -65,10 +63,7 @@ class TimestepEncoder(fl.Passthrough):
     """Writes ``range_adapter.<context_key>`` = MLP(sinusoid(timestep)) + TextTimeEmbedding."""
 
     def __init__(
-        self,
-        context_key: str = "timestep_embedding",
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, context_key: str = "timestep_embedding", device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
         self.timestep_embedding_dim = 1280
         super().__init__(
@@ -97,12 +92,8 @@ class TimestepEncoder(fl.Passthrough):
 
 class SDXLCrossAttention(CrossAttentionBlock2d):
     def __init__(
-        self,
-        channels: int,
-        num_attention_layers: int = 1,
-        num_attention_heads: int = 10,
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, channels: int, num_attention_layers: int = 1, num_attention_heads: int = 10,
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
         super().__init__(
             channels=channels,

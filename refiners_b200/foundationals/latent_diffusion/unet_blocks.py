@@ -24,20 +24,12 @@ class ResidualBlock(fl.Sum):
     later by injecting a RangeAdapter2d around the first conv."""
 
     def __init__(
-        self,
-        in_channels: int,
-        out_channels: int,
-        num_groups: int = 32,
-        eps: float = 1e-5,
-        device: Device | str | None = None,
-        dtype: DType | None = None,
+        self, in_channels: int, out_channels: int, num_groups: int = 32, eps: float = 1e-5,
+        device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
         if in_channels % num_groups != 0 or out_channels % num_groups != 0:
             raise ValueError("Number of input and output channels must be divisible by num_groups.")
-        self.in_channels = in_channels
-        self.out_channels = out_channels
-        self.num_groups = num_groups
-        self.eps = eps
+        self.in_channels, self.out_channels, self.num_groups, self.eps = in_channels, out_channels, num_groups, eps
         kw = dict(device=device, dtype=dtype)
         # the shortcut is built first so that seeded random init draws in the reference's order
         shortcut = fl.Identity() if in_channels == out_channels else fl.Conv2d(in_channels, out_channels, kernel_size=1, **kw)
