@@ -155,6 +155,8 @@ class IPAdapter(Generic[T], fl.Chain, Adapter[T]):
         self.fine_grained = fine_grained
         # list-wrapped: these are not part of the UNet's state dict
         self._clip_image_encoder = [clip_image_encoder]
+        if fine_grained and clip_image_encoder is not None:
+            self._grid_image_encoder = [self.convert_to_grid_features(clip_image_encoder)]
         self._image_proj = [image_proj]
         self.sub_adapters = [
             CrossAttentionAdapter(target=attn, scale=scale)
@@ -205,6 +207,68 @@ class IPAdapter(Generic[T], fl.Chain, Adapter[T]):
     def set_clip_image_embedding(self, image_embedding: Tensor) -> None:
         """[B, T, C] image tokens read by every `ImageCrossAttention` (T = 4, or 16 fine-grained)."""
         self.set_context("ip_adapter", {"clip_image_embedding": image_embedding})
+
+    # ---- once per image prompt (outside the denoising loop): image(s) -> the context tensor above
+    @property
+    def grid_image_encoder(self) -> fl.Chain:
+        assert hasattr(self, "_grid_image_encoder"), "fine-grained prompts need a CLIP image encoder at construction"
+        return self._grid_image_encoder[0]
+
+    @staticmethod
+    def convert_to_grid_features(clip_image_encoder: fl.Chain) -> fl.Chain:
+        """The encoder truncated to patch features for the PerceiverResampler: a structural copy (shared weights)
+        without [CLS] pooling, final LayerNorm and projection, and without the last transformer layer - the
+        penultimate hidden states of ViT-H (image_prompt.py:553-565 in the reference)."""
+        grid = clip_image_encoder.structural_copy()
+        assert isinstance(grid[-1], fl.Linear) and isinstance(grid[-2], fl.LayerNorm) and isinstance(grid[-3], fl.Lambda)
+        for _ in range(3):
+            grid.pop()
+        layers = grid[-1]
+        assert isinstance(layers, fl.Chain) and len(layers) == 32
+        layers.pop()
+        return grid
+
+    def preprocess_image(
+        self, image: Any, size: tuple[int, int] = (224, 224), mean: list[float] | None = None, std: list[float] | None = None,
+    ) -> Tensor:
+        """PIL image -> ``[1, 3, H, W]`` resized and normalised with OpenAI CLIP's statistics, on the UNet's device/dtype."""
+        from refiners_b200.fluxion.utils import image_to_tensor
+
+        pixels = image_to_tensor(image.resize(size), device=self.target.device, dtype=self.target.dtype)
+        stats = lambda values: torch.tensor(values, device=pixels.device, dtype=pixels.dtype).reshape(1, -1, 1, 1)  # noqa: E731
+        mean = [0.48145466, 0.4578275, 0.40821073] if mean is None else mean
+        std = [0.26862954, 0.26130258, 0.27577711] if std is None else std
+        return (pixels - stats(mean)) / stats(std)
+
+    def _compute_clip_image_embedding(self, image_prompt: Tensor) -> tuple[Tensor, Tensor]:
+        encoder = self.grid_image_encoder if self.fine_grained else self.clip_image_encoder
+        features = encoder(image_prompt)
+        conditional = self.image_proj(features)
+        # the unconditional prompt: a zero embedding (plain) or the features of a black image (fine-grained)
+        blank = encoder(torch.zeros_like(image_prompt)) if self.fine_grained else torch.zeros_like(features)
+        return self.image_proj(blank), conditional
+
+    def compute_clip_image_embedding(
+        self, image_prompt: Any, weights: list[float] | None = None, concat_batches: bool = True,
+    ) -> Tensor:
+        """Image prompt(s) (PIL image, list of PIL images, or a preprocessed tensor) -> the ``[2, T', C]`` (or
+        ``[2B, T, C]``) tensor for `set_clip_image_embedding`, unconditional half first.  ``weights`` scale each
+        image's conditional tokens; ``concat_batches`` joins several images into one longer token sequence
+        (image_prompt.py:457-511 in the reference)."""
+        if isinstance(image_prompt, list):
+            image_prompt = torch.cat([self.preprocess_image(image) for image in image_prompt])
+        elif not isinstance(image_prompt, Tensor):
+            image_prompt = self.preprocess_image(image_prompt)
+        negative, conditional = self._compute_clip_image_embedding(image_prompt)
+        count = image_prompt.shape[0]
+        if weights is not None:
+            assert len(weights) == count, f"Got {len(weights)} weights for {count} images"
+            if any(w != 1.0 for w in weights):
+                conditional *= torch.tensor(weights, device=conditional.device, dtype=conditional.dtype).unsqueeze(-1).unsqueeze(-1)
+        if count > 1 and concat_batches:
+            negative = torch.cat(negative.chunk(count), dim=1)
+            conditional = torch.cat(conditional.chunk(count), dim=1)
+        return torch.cat((negative, conditional))
 
     def project_image_embedding(self, clip_embedding: Tensor, negative: Tensor | None = None) -> Tensor:
         """image_proj(clip embedding), with the unconditional half first when given

@@ -100,6 +100,37 @@ def test_ip_adapter_plus_perceiver_resampler(ref):
         assert torch.equal(mine(x), theirs(x))
 
 
+def test_clip_image_encoder_and_image_embedding(ref):
+    """CLIP vision tower (structure of H; numbers on a tiny tower with the reference's weights) and the IP-Adapter's
+    once-per-prompt path image -> context tensor, including weights and token concatenation."""
+    import refiners.fluxion.layers as rfl
+    from refiners.foundationals.clip.image_encoder import CLIPImageEncoder as REnc, CLIPImageEncoderH as REncH
+    from refiners.foundationals.latent_diffusion.cross_attention import CrossAttentionBlock2d as RBlock
+    from refiners.foundationals.latent_diffusion.image_prompt import ImageProjection as RProj, IPAdapter as RIP
+
+    import refiners_b200.fluxion.layers as fl
+    from refiners_b200.foundationals.clip import CLIPImageEncoder, CLIPImageEncoderH
+    from refiners_b200.foundationals.latent_diffusion import CrossAttentionBlock2d
+    from refiners_b200.foundationals.latent_diffusion.image_prompt import ImageProjection, IPAdapter
+
+    mine_h, theirs_h = CLIPImageEncoderH(device="meta"), REncH(device="meta")
+    same(mine_h, theirs_h)
+    same(IPAdapter.convert_to_grid_features(mine_h), RIP.convert_to_grid_features(theirs_h))
+
+    cfg = dict(image_size=32, embedding_dim=48, output_dim=24, patch_size=8, num_layers=2, num_attention_heads=3, feedforward_dim=96)
+    block = dict(channels=64, context_embedding_dim=40, context_key="ctx", num_attention_heads=2, use_linear_projection=True)
+    torch.manual_seed(0)
+    enc_r, proj_r, tgt_r = REnc(**cfg), RProj(clip_image_embedding_dim=24, clip_text_embedding_dim=40), rfl.Chain(RBlock(**block))
+    enc_m, proj_m, tgt_m = CLIPImageEncoder(**cfg), ImageProjection(clip_image_embedding_dim=24, clip_text_embedding_dim=40), fl.Chain(CrossAttentionBlock2d(**block))
+    enc_m.load_state_dict(enc_r.state_dict()), proj_m.load_state_dict(proj_r.state_dict())
+    ip_r, ip_m = RIP(tgt_r, enc_r, proj_r), IPAdapter(tgt_m, enc_m, proj_m)
+    images = torch.randn(3, 3, 32, 32)
+    with torch.no_grad():
+        assert torch.equal(enc_m(images), enc_r(images))
+        for kwargs in ({}, {"weights": [1.0, 0.5, 2.0]}, {"concat_batches": False}):
+            assert torch.equal(ip_m.compute_clip_image_embedding(images, **kwargs), ip_r.compute_clip_image_embedding(images, **kwargs))
+
+
 def test_lora_adapters_on_cross_attention(ref):
     import refiners.fluxion.layers as rfl
     from refiners.fluxion.adapters.lora import LinearLora as RLora, LoraAdapter as RAdapter
