@@ -111,7 +111,7 @@ def sdpa(q: Tensor, k: Tensor, v: Tensor, num_heads: int, is_causal: bool = Fals
         return o.transpose(1, 2).reshape(B, Sq, C)
     logits = (qh @ kh.transpose(-1, -2)) / math.sqrt(d)
     if is_causal:
-        mask = torch.ones(Sq, Sk, dtype=torch.bool).tril()
+        mask = torch.ones(Sq, Sk, dtype=torch.bool, device=q.device).tril()
         logits = logits.masked_fill(~mask, float("-inf"))
     logits = logits - logits.max(dim=-1, keepdim=True).values
     p = torch.exp(logits)
@@ -131,7 +131,7 @@ def lora_linear(x: Tensor, weight: Tensor, bias: Tensor | None, loras: list[tupl
 def sinusoidal_embedding(x: Tensor, embedding_dim: int) -> Tensor:
     """cos | sin of x * 10000^(-i/half).  Reference: latent_diffusion/range_adapter.py:11-22."""
     half = embedding_dim // 2
-    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half
+    exponent = -math.log(10000) * torch.arange(0, half, dtype=torch.float32, device=x.device) / half
     emb = x.unsqueeze(1).float() * torch.exp(exponent).unsqueeze(0)
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
@@ -140,6 +140,6 @@ def nearest_upsample(x: Tensor, size: tuple[int, int]) -> Tensor:
     """Nearest-neighbour resize (index = floor(dst * in / out)).
     Reference: fluxion/layers/sampling.py:13-38 via fluxion/utils.py interpolate."""
     H, W = x.shape[-2:]
-    hi = (torch.arange(size[0]) * H) // size[0]
-    wi = (torch.arange(size[1]) * W) // size[1]
+    hi = (torch.arange(size[0], device=x.device) * H) // size[0]
+    wi = (torch.arange(size[1], device=x.device) * W) // size[1]
     return x[..., hi[:, None], wi[None, :]]

@@ -208,6 +208,102 @@ def pin_dinov2(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'dinov2.safetensors'}")
 
 
+def pin_full_size(write: bool) -> None:
+    """BASELINE-size cases (oracle/cases.py): SDXLUNet at 128x128 latents plain (config 2), with 700 LoRA
+    adapters + IP-Adapter (config 3), with ControlLora (config 4), one full StableDiffusion_XL step with CFG +
+    Euler at three steps (A17) and the SAM ViT-H encoder on a 1024^2 image (config 5).  Inputs and adapter
+    weights are keyed (regenerated anywhere); only the reference's outputs are stored.
+    ``--cases=cfg2,step,cfg3,cfg4,cfg5`` re-records a subset and merges it into the existing file."""
+    _import_reference()
+    import gc
+    import time
+
+    from safetensors.torch import load_file, save_file
+
+    from oracle import cases
+    from oracle import euler as oeuler
+    from oracle import sam as osam
+    from oracle import unet as ounet
+
+    api = cases.reference_api()
+    path = GOLDEN / "full_size.safetensors"
+    fx: dict[str, torch.Tensor] = load_file(str(path)) if path.exists() else {}
+    wanted = next((a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--cases=")), ["cfg2", "step", "cfg3", "cfg4", "cfg5"])
+    t0 = time.time()
+
+    def save() -> None:
+        print(f"  ({time.time() - t0:.0f} s)")
+        if write:
+            GOLDEN.mkdir(parents=True, exist_ok=True)
+            save_file({k: v.contiguous() for k, v in fx.items()}, str(path))
+            print(f"  wrote {path}: {sorted(fx)}")
+
+    with torch.no_grad():
+        base = cases.sdxl_base_weights(api) if set(wanted) - {"cfg5"} else {}
+        print(f"full size: base weights ready ({time.time() - t0:.0f} s)")
+
+        if {"cfg2", "step", "cfg3"} & set(wanted):
+            unet = cases.build_sdxl(api, base)
+            if "cfg2" in wanted:
+                inp = cases.sdxl_inputs("cfg2", 2)
+                cases.set_sdxl_contexts(unet, inp)
+                y = unet(inp["x"])
+                fx["cfg2.y"] = y
+                _close("config 2: SDXLUNet 128x128 B=2", ounet.sdxl_unet(base, inp["x"], inp["timestep"], inp["ctx"], inp["pooled"], inp["time_ids"]), y)
+                save()
+            if "step" in wanted:  # StableDiffusion_XL step (A17) on the plain UNet
+                sdxl = api.StableDiffusion_XL(unet=unet, solver=api.Euler(num_inference_steps=30))
+                sin = cases.step_inputs()
+                x0 = sin["x"] * float(sdxl.solver.init_noise_sigma)
+                schedule = oeuler.EulerSchedule(30)
+                for step, scale in cases.STEP_CASES:
+                    y = sdxl(x0, step=step, clip_text_embedding=sin["ctx"], pooled_text_embedding=sin["pooled"], time_ids=sin["time_ids"],
+                             condition_scale=scale)
+                    fx[f"step.y_{step}"] = y
+                    mine = oeuler.denoise_step(
+                        lambda lat, ts: ounet.sdxl_unet(base, lat, ts, sin["ctx"], sin["pooled"], sin["time_ids"]), schedule, x0, step, scale)
+                    _close(f"StableDiffusion_XL step {step} (scale {scale})", mine, y)
+                del sdxl
+                save()
+            if "cfg3" in wanted:  # adapters injected into the same UNet
+                inp = cases.sdxl_inputs("cfg3", 2)
+                ip, extra = cases.attach_config3(api, unet, 2)
+                assert extra["n_lora_adapters"] == 700, extra["n_lora_adapters"]
+                cases.set_sdxl_contexts(unet, inp)
+                y = unet(inp["x"])
+                fx["cfg3.y"] = y
+                w3 = ounet.Weights(base, loras=extra["loras"], ip=extra["ip"], ip_scale=extra["ip_scale"], ip_embedding=extra["ip_embedding"])
+                _close("config 3: + 700 LoRA adapters + IP-Adapter", ounet.sdxl_unet(w3, inp["x"], inp["timestep"], inp["ctx"], inp["pooled"], inp["time_ids"]), y)
+                del ip, w3, extra
+                save()
+            del unet
+            gc.collect()
+
+        if "cfg4" in wanted:
+            inp = cases.sdxl_inputs("cfg4", 2)
+            unet = cases.build_sdxl(api, base)
+            adapter, extra = cases.attach_config4(api, unet, 2)
+            cases.set_sdxl_contexts(unet, inp)
+            y = unet(inp["x"])
+            fx["cfg4.y"] = y
+            wc = ounet.Weights(base, loras=extra["loras"])
+            args = (inp["timestep"], inp["ctx"], inp["pooled"], inp["time_ids"])
+            deltas = ounet.sdxl_control_lora(wc, extra["own"], inp["x"], *args, extra["condition"], scale=extra["scale"])
+            _close(f"config 4: + ControlLora ({extra['n_loras']} LoRAs)", ounet.sdxl_unet(base, inp["x"], *args, residuals=deltas), y)
+            del unet, adapter, wc, extra, deltas
+            save()
+        del base
+        gc.collect()
+
+        if "cfg5" in wanted:
+            sam, sd = cases.build_sam(api)
+            img = cases.sam_inputs()
+            y = sam(img)
+            fx["cfg5.y"] = y
+            _close("config 5: SAMViTH 1024^2", osam.sam_vit(sd, img, num_layers=32, heads=16, global_indices=(7, 15, 23, 31)), y)
+            save()
+
+
 def main(write: bool) -> None:
     rfl = _import_reference()
     from safetensors.torch import save_file
@@ -440,6 +536,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-dinov2": pin_dinov2,
+        "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]
     if chosen:

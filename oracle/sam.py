@@ -29,8 +29,9 @@ def relative_position_attention(qkv: Tensor, horizontal_embedding: Tensor, verti
     d = C // heads
     t = qkv.reshape(B, H * W, 3, heads, d).permute(2, 0, 3, 1, 4).reshape(3, B * heads, H * W, d)
     q, k, v = t[0], t[1], t[2]
-    ih = torch.arange(H)[:, None] - torch.arange(H)[None, :] + H - 1
-    iw = torch.arange(W)[:, None] - torch.arange(W)[None, :] + W - 1
+    ah, aw = torch.arange(H, device=qkv.device), torch.arange(W, device=qkv.device)
+    ih = ah[:, None] - ah[None, :] + H - 1
+    iw = aw[:, None] - aw[None, :] + W - 1
     q5 = q.reshape(B * heads, H, W, d)
     rel_v = torch.einsum("bhwc,hkc->bhwk", q5, vertical_embedding[ih])   # [B', H, W, Hk]
     rel_h = torch.einsum("bhwc,wkc->bhwk", q5, horizontal_embedding[iw])  # [B', H, W, Wk]

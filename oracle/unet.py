@@ -24,7 +24,28 @@ from oracle import ops
 SD = Mapping[str, Tensor]
 
 
+class Weights(dict):
+    """A state dict (reference keys) plus the adapter weights that the reference keeps in injected
+    modules.  Everything is addressed by the ORIGINAL path of the adapted leaf, so the restatement does
+    not depend on how an adapter renames its target's state-dict key:
+      loras[path]  list of (down [r, in], up [out, r], scale) on the Linear at ``path``
+                   (fluxion/adapters/lora.py:383-448: Sum(target, Chain(down, up, Multiply(scale))...))
+      ip[path]     (W_k', W_v') of the IP-Adapter ImageCrossAttention on the Attention at ``path``
+                   (latent_diffusion/image_prompt.py:237-309), with ``ip_scale`` and ``ip_embedding``."""
+
+    def __init__(self, tensors: Mapping[str, Tensor], loras: dict | None = None, ip: dict | None = None,
+                 ip_scale: float = 1.0, ip_embedding: Tensor | None = None) -> None:
+        super().__init__(tensors)
+        self.loras = loras or {}
+        self.ip = ip or {}
+        self.ip_scale = ip_scale
+        self.ip_embedding = ip_embedding
+
+
 def _lin(sd: SD, prefix: str, x: Tensor) -> Tensor:
+    loras = getattr(sd, "loras", None)
+    if loras and prefix in loras:
+        return ops.lora_linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"), loras[prefix])
     return ops.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
 
 
@@ -58,7 +79,15 @@ def attention(sd: SD, prefix: str, q_in: Tensor, kv_in: Tensor, heads: int) -> T
     q = _lin(sd, prefix + ".Distribute.Linear_1", q_in)
     k = _lin(sd, prefix + ".Distribute.Linear_2", kv_in)
     v = _lin(sd, prefix + ".Distribute.Linear_3", kv_in)
-    return _lin(sd, prefix + ".Linear", ops.sdpa(q, k, v, heads))
+    o = ops.sdpa(q, k, v, heads)
+    ip = getattr(sd, "ip", None)
+    if ip and prefix in ip:
+        # CrossAttentionAdapter (image_prompt.py:312-347): the SDPA becomes Sum(SDPA(q, k, v),
+        # Chain(SDPA(q, W_k' e, W_v' e), Multiply(scale))) in front of the output projection
+        wk, wv = ip[prefix]
+        e = sd.ip_embedding  # type: ignore[attr-defined]
+        o = o + sd.ip_scale * ops.sdpa(q, ops.linear(e, wk), ops.linear(e, wv), heads)  # type: ignore[attr-defined]
+    return _lin(sd, prefix + ".Linear", o)
 
 
 def cross_attention_block(sd: SD, prefix: str, x: Tensor, context: Tensor, heads: int) -> Tensor:
@@ -206,10 +235,49 @@ def sdxl_timestep_embedding(sd: SD, timestep: Tensor, pooled_text_embedding: Ten
     return t + tt
 
 
+def sdxl_control_lora(
+    sd: SD, own: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor,
+    condition: Tensor, scale: float = 1.0,
+) -> list[Tensor]:
+    """ControlLora (stable_diffusion_xl/control_lora.py:144-248): a structural copy of TimestepEncoder +
+    DownBlocks + MiddleBlock whose weighted leaves are the UNet's own, with LoRAs attached inside the copy
+    only (``sd.loras``, keyed by the leaf's path inside the copy), the encoded condition added at the end of
+    the first block (:190-202) and a 1x1 ZeroConvolution after each of the 9 down entries and after the middle
+    block contributing ``scale * conv(h)`` to residual slot n (:90-132, :203-233).  ``own`` holds the copy's
+    own parameters (ConditionEncoder, ZeroConvolutions) under their paths inside the copy."""
+    dtype = x.dtype
+    temb = sdxl_timestep_embedding(sd, timestep, pooled_text_embedding, time_ids, dtype)
+    deltas: list[Tensor] = []
+    h = x
+    for i, entry in enumerate(_SDXL_DOWN):
+        p = f"DownBlocks.Chain_{i + 1}"
+        if entry[0] == "in":
+            h = _conv(sd, p + ".Conv2d", h, padding=1)
+        elif entry[0] == "down":
+            h = _conv(sd, p + ".Downsample.Conv2d", h, stride=2, padding=1)
+        else:
+            h = residual_block(sd, p + ".ResidualBlock", h, temb)
+            if entry[1]:
+                h = cross_attention_2d(sd, p + ".SDXLCrossAttention", h, clip_text_embedding, entry[2], entry[1], True)
+        deltas.append(_conv(own, p + ".ZeroConvolution.Conv2d", h) * scale)
+        if entry[0] == "in":
+            # the condition Residual is APPENDED to the first block (control_lora.py:190-202), i.e. it sits after the
+            # accumulator that becomes ZeroConvolution 0: tap 0 sees conv_in(x) without the condition
+            h = h + condition_encoder(own, p + ".Residual.ConditionEncoder", condition)
+    m = "MiddleBlock"
+    h = residual_block(sd, m + ".ResidualBlock_1", h, temb)
+    h = cross_attention_2d(sd, m + ".SDXLCrossAttention", h, clip_text_embedding, 20, 10, True)
+    h = residual_block(sd, m + ".ResidualBlock_2", h, temb)
+    deltas.append(_conv(own, m + ".ZeroConvolution.Conv2d", h) * scale)
+    return deltas
+
+
 def sdxl_unet(
-    sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor
+    sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor,
+    residuals: list[Tensor] | None = None,
 ) -> Tensor:
-    """SDXLUNet forward (sdxl/unet.py:258-351)."""
+    """SDXLUNet forward (sdxl/unet.py:258-351).  ``residuals``: the 10 ControlLora corrections already sitting
+    in the residual slots when the UNet runs (the control copy is child 0 of the UNet, control_lora.py:283-286)."""
     dtype = x.dtype
     temb = sdxl_timestep_embedding(sd, timestep, pooled_text_embedding, time_ids, dtype)
     skips: list[Tensor] = []
@@ -224,12 +292,13 @@ def sdxl_unet(
             h = residual_block(sd, p + ".ResidualBlock", h, temb)
             if entry[1]:
                 h = cross_attention_2d(sd, p + ".SDXLCrossAttention", h, clip_text_embedding, entry[2], entry[1], True)
-        skips.append(h)
+        skips.append(h if residuals is None else h + residuals[i])  # ResidualAccumulator is a Passthrough
     m = "MiddleBlock"
     h = residual_block(sd, m + ".ResidualBlock_1", h, temb)
     h = cross_attention_2d(sd, m + ".SDXLCrossAttention", h, clip_text_embedding, 20, 10, True)
     h = residual_block(sd, m + ".ResidualBlock_2", h, temb)
-    h = h + 0.0  # Residual(UseContext residuals[-1]): the spare 10th slot keeps its initial 0.0
+    # Residual(UseContext residuals[-1]): the spare 10th slot keeps its initial 0.0 unless ControlLora wrote it
+    h = h + (0.0 if residuals is None else residuals[9])
     for n, (layers, heads, up) in enumerate(_SDXL_UP):
         p = f"UpBlocks.Chain_{n + 1}"
         h = torch.cat([h, skips[-n - 1]], dim=1)  # ResidualConcatenator(-n-2) on a list with one spare slot

@@ -217,10 +217,8 @@ _concat_cache = _PackCache()
 
 
 def clear_caches() -> None:
-    _conv_cache.clear()
-    _geglu_cache.clear()
-    _lora_cache.clear()
-    _concat_cache.clear()
+    for cache in (_conv_cache, _conv_pad_cache, _patch_cache, _geglu_cache, _lora_cache, _concat_cache):
+        cache.clear()
 
 
 # ------------------------------------------------------------------------- raw op kernels
@@ -540,6 +538,22 @@ def _window_merge_impl(x: Tensor, window: int, height: int, width: int) -> Tenso
     return y
 
 
+def _on_operand_device(fn: Any) -> Any:
+    """Run an op with the first tensor operand's device current: ``_stream()``, the allocations and the
+    library's per-device state (shared-memory opt-in, SM count) all follow the operands, not whatever
+    device happened to be current (a model on cuda:1, two GPUs in one process)."""
+
+    def run(*args: Any) -> Any:
+        first = args[0][0] if isinstance(args[0], (list, tuple)) else args[0]
+        if first.device.index == torch.cuda.current_device():
+            return fn(*args)
+        with torch.cuda.device(first.device):
+            return fn(*args)
+
+    run.__name__ = fn.__name__
+    return run
+
+
 # --------------------------------------------------------------- torch custom-op registration
 _torch_lib = torch.library.Library("refiners_b200", "DEF")
 _torch_lib.define(
@@ -583,7 +597,7 @@ for _name, _fn in (
     ("window_partition", _window_partition_impl),
     ("window_merge", _window_merge_impl),
 ):
-    _torch_lib.impl(_name, _fn, "CUDA")
+    _torch_lib.impl(_name, _on_operand_device(_fn), "CUDA")
 
 
 @torch.library.register_fake("refiners_b200::linear")

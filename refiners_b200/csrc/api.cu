@@ -23,14 +23,21 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int kernel_mode() { return g_mode.load(std::memory_order_relaxed); }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+  return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
+// SM count of the CURRENT device (cached per ordinal: a process may drive several GPUs)
 int sm_count() {
-  static int cached = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    return n;
-  }();
-  return cached;
+  static std::atomic<int> cached[kMaxDevices];
+  const int dev = current_device();
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  cached[dev].store(n, std::memory_order_relaxed);
+  return n;
 }
 
 // implemented in norm_kernels.cu
@@ -255,7 +262,10 @@ int rb200_sdpa(void* stream, int dtype, const void* q, const void* k, const void
   p.scale = scale; p.causal = is_causal;
   p.k2 = k2; p.v2 = v2; p.Sk2 = Sk2; p.k2_sb = k2_sb; p.k2_ss = k2_ss; p.v2_sb = v2_sb; p.v2_ss = v2_ss; p.scale2 = scale2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (kernel_mode() != 1 && tc_sdpa_supported(p)) return tc_sdpa(st, p);
+  if (kernel_mode() != 1) {
+    if (tc_sdpa2_supported(p)) return tc_sdpa2(st, p);
+    if (tc_sdpa_supported(p)) return tc_sdpa(st, p);
+  }
   return simt_sdpa(st, p);
 }
 

@@ -110,7 +110,16 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t dtype_size(int dtype) { return dtype == RB200_FP32 ? 4 : 2; }
-int sm_count();  // cached (api.cu)
+constexpr int kMaxDevices = 64;
+int current_device();  // ordinal of the current CUDA device, clamped to [0, kMaxDevices)
+int sm_count();        // of the current device, cached per ordinal (api.cu)
+
+// One-time per-device set-up of a kernel (cudaFuncSetAttribute is per device): `if (once.needed()) {...; once.done();}`
+struct PerDeviceOnce {
+  bool flag[kMaxDevices] = {};
+  bool needed() const { return !flag[current_device()]; }
+  void done() { flag[current_device()] = true; }
+};
 
 // ---------------------------------------------------------- kernel families (one .cu each)
 // GEMM / conv problem handed from api.cu to the SIMT or tcgen05 implementation.
@@ -151,5 +160,8 @@ struct SdpaProblem {
 int simt_sdpa(cudaStream_t st, const SdpaProblem& p);
 bool tc_sdpa_supported(const SdpaProblem& p);
 int tc_sdpa(cudaStream_t st, const SdpaProblem& p);
+// second-generation kernel (tc_attention2.cu): head dim <= 64, one K/V set, no bias, Sq > 128
+bool tc_sdpa2_supported(const SdpaProblem& p);
+int tc_sdpa2(cudaStream_t st, const SdpaProblem& p);
 
 }  // namespace rb200

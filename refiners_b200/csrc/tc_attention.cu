@@ -680,13 +680,13 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
 template <typename T, bool DUAL, int HD, bool BIAS, bool LAZY = false>
 int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
            const CUtensorMap& mv2, const AttnParams& prm) {
-  static bool configured = false;
+  static PerDeviceOnce configured;
   constexpr size_t SMEM_MAX = Cfg<HD>::SMEM_BYTES + (BIAS ? MAX_BIAS_BYTES : 0);
   const size_t SMEM = Cfg<HD>::SMEM_BYTES + (BIAS ? prm.bias_bytes : 0);
-  if (!configured) {
+  if (configured.needed()) {
     if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_MAX)) != cudaSuccess)
       RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM_MAX);
-    configured = true;
+    configured.done();
   }
   const int64_t cap = int64_t(sm_count()) * Cfg<HD>::CTAS_PER_SM;
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);

@@ -1,0 +1,465 @@
+// tcgen05 flash attention, second generation: the self- / cross-attention of the SDXL transformer blocks
+// (head dim <= 64, bf16 / fp16, non-causal, one K/V set, no bias, Sq > 128).  tc_attention.cu keeps every other case
+// (head dim 128, SAM's relative-position bias, IP-Adapter's second K/V set, tiny Sq).
+//
+//   O[b, q, h, :] = softmax(Q K^T * scale) V        replaces fluxion/layers/attentions.py:115-202 of the reference
+//
+// What changed against the first kernel, and why (ncu of round 1: tensor pipe 22 %, XU 34 %, issue 38 % - a latency chain):
+//   * ONE persistent CTA per SM owns a PAIR of 128-query tiles of one (batch, head): both tiles share every K/V tile
+//     that TMA brings in (half the L2 -> smem traffic per flop: two CTAs per SM each streaming their own K/V would need
+//     ~15 TB/s of L2 bandwidth at 1 PFLOP/s).
+//   * 128 keys per tile: S = Q K^T is a UMMA 128 x 128 x 16 (full-rate instruction shape), P V a 128 x 64 x 16 over 8 k-steps.
+//   * two softmax warpgroups, one per query tile, ping-pong against one MMA-issuing thread: while group A exponentiates
+//     tile j the tensor core computes S_B(j) / P_B V, and vice versa.
+//   * the running output never leaves TMEM: the P V MMAs accumulate into one O tile per group, and the softmax keeps a
+//     STALE running maximum - O is rescaled in TMEM (tcgen05.ld / st) only when a row's maximum grows by more than 2^8
+//     (FlashAttention-4's conditional rescaling); the first kernel read 64 fp32 columns of O_j back per thread per tile.
+//   * S is read from TMEM exactly once per tile into registers (128 fp32 per thread; the softmax warpgroups raise their
+//     register budget with setmaxnreg, the TMA / MMA warpgroup gives its registers away).
+//   * optionally (POLY) every fourth exponential runs as a Cody-Waite cubic on the FMA pipe instead of MUFU.EX2: at head
+//     dim 64 the exponentials, not the MMAs, bound the kernel (16 MUFU lanes / clk / SM against 4096 MAC / clk / SM).
+//
+// Warps: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-3: idle}; warpgroup 1 = softmax of
+// query tile A; warpgroup 2 = softmax of query tile B.  thread = query row = TMEM lane.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+// smem: Q 2 x (2 x 16 KB) (double buffered across work items), K/V ring 3 x (16 + 16 KB), P_A, P_B 32 KB each.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace rb200 {
+namespace {
+
+using namespace ptx;
+
+constexpr int QT = 128;             // queries per tile (UMMA M)
+constexpr int KT = 128;             // keys per tile (UMMA N of S, K extent of P V)
+constexpr int HD = 64;              // head-dim slab (columns >= D are zero filled by TMA)
+constexpr int STAGES = 3;
+constexpr int NUM_THREADS = 384;
+constexpr int Q_TILE_BYTES = QT * HD * 2;      // 16 KB
+constexpr int Q_BYTES = 2 * Q_TILE_BYTES;      // both tiles of a pair
+constexpr int K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2;
+constexpr int P_SLAB = QT * 64 * 2;            // 64 keys of P for 128 rows: one 128-byte-row swizzle slab
+constexpr int P_BYTES = 2 * P_SLAB;            // 128 keys
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr float RESCALE_LOG2 = 8.0f;           // tolerate a stale maximum until a probability could exceed 2^8
+
+struct Attn2Params {
+  void* o;
+  int64_t o_sb, o_ss;
+  int H;
+  int64_t Sq, Sk;
+  int n_pairs;          // ceil(Sq / 256)
+  int64_t total_work;   // B * H * n_pairs
+  int ntiles;           // ceil(Sk / 128)
+  float scale_log2e;
+  uint32_t idesc_qk, idesc_pv;
+  int d_out;
+};
+
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <typename T, bool POLY>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const Attn2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                           // [2 buffers][2 tiles][128 x 64]
+  uint8_t* sK = sQ + 2 * Q_BYTES;               // [STAGES][128 x 64]
+  uint8_t* sV = sK + STAGES * K_BYTES;
+  uint8_t* sP = sV + STAGES * V_BYTES;          // [2 groups][2 slabs][128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint64_t* kv_full = bars;                     // [STAGES] TMA -> MMA
+  uint64_t* kv_empty = bars + STAGES;           // [STAGES] MMA -> TMA
+  uint64_t* q_full = bars + 2 * STAGES;         // [2]
+  uint64_t* q_empty = q_full + 2;               // [2]
+  uint64_t* bar_s = q_full + 4;                 // [2 groups] S tile of the group is in TMEM
+  uint64_t* bar_sfree = q_full + 6;             // [2] the group has read its S tile into registers
+  uint64_t* bar_p = q_full + 8;                 // [2] P tile of the group is in smem (and O has been rescaled if needed)
+  uint64_t* bar_o = q_full + 10;                // [2] every P V issued so far for the group has landed in O
+  uint64_t* bar_ofree = q_full + 12;            // [2] the finished work item's O rows have been read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wg = warp >> 2;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_k);
+    prefetch_tmap(&map_v);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+      mbar_init(&bar_s[b], 1);
+      mbar_init(&bar_sfree[b], 4);
+      mbar_init(&bar_p[b], 4);
+      mbar_init(&bar_o[b], 1);
+      mbar_init(&bar_ofree[b], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (wg == 0) {
+    setmaxnreg_dec<72>();
+    if (warp == 0) {
+      // ================================================================================ TMA
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t n = 0;  // work items of this CTA so far: Q buffer = n & 1, its phase = (n >> 1) & 1
+        for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
+          const int pair = int(w % p.n_pairs);
+          const int h = int((w / p.n_pairs) % p.H);
+          const int b = int(w / (int64_t(p.n_pairs) * p.H));
+          const uint32_t qb = n & 1, qph = (n >> 1) & 1;
+          mbar_wait(&q_empty[qb], qph ^ 1, 1);
+          mbar_arrive_expect_tx(&q_full[qb], Q_BYTES);
+          tma_load_4d(sQ + qb * Q_BYTES, &map_q, &q_full[qb], 0, h, pair * 2 * QT, b);
+          tma_load_4d(sQ + qb * Q_BYTES + Q_TILE_BYTES, &map_q, &q_full[qb], 0, h, pair * 2 * QT + QT, b);
+          for (int j = 0; j < p.ntiles; ++j) {
+            mbar_wait(&kv_empty[stage], phase ^ 1, 2);
+            mbar_arrive_expect_tx(&kv_full[stage], K_BYTES + V_BYTES);
+            tma_load_4d(sK + stage * K_BYTES, &map_k, &kv_full[stage], 0, h, j * KT, b);
+            tma_load_4d(sV + stage * V_BYTES, &map_v, &kv_full[stage], 0, h, j * KT, b);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================================================================ MMA
+      if (lane == 0) {
+        int st_k = 0, st_v = 0;     // ring cursors: stage whose K feeds the next S pair / whose V feeds the next P V pair
+        uint32_t ph_k = 0;
+        uint32_t t[2] = {0, 0};     // tiles issued per group so far (barrier phases of bar_s / bar_p / bar_o / bar_sfree)
+        uint32_t n = 0;
+        // S_g(tile) = Q_g K^T: the K stage must have landed (checked once per tile by the caller) and the group must have
+        // read its previous S tile out of TMEM
+        auto issue_s = [&](int g, uint32_t qb, int stage_k, uint32_t tiles_done) {
+          if (tiles_done > 0) mbar_wait(&bar_sfree[g], (tiles_done - 1) & 1, 4);
+          tcgen05_fence_after();
+          const uint64_t dq = desc_kmajor(smem_u32(sQ + qb * Q_BYTES + g * Q_TILE_BYTES));
+          const uint64_t dk = desc_kmajor(smem_u32(sK + stage_k * K_BYTES));
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base + g * 128, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+          umma_commit(&bar_s[g]);
+        };
+        uint32_t s_issued[2] = {0, 0};  // S tiles issued per group (runs one ahead of t[g])
+        for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
+          const uint32_t qb = n & 1, qph = (n >> 1) & 1;
+          mbar_wait(&q_full[qb], qph, 5);
+          mbar_wait(&kv_full[st_k], ph_k, 3);
+          issue_s(0, qb, st_k, s_issued[0]++);
+          issue_s(1, qb, st_k, s_issued[1]++);
+          if (++st_k == STAGES) {
+            st_k = 0;
+            ph_k ^= 1;
+          }
+          for (int j = 0; j < p.ntiles; ++j) {
+            const bool more = j + 1 < p.ntiles;
+            if (more) mbar_wait(&kv_full[st_k], ph_k, 6);  // K_{j+1} for the S tiles issued below
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              mbar_wait(&bar_p[g], t[g] & 1, 7);  // P_g(j) is in smem; O_g has been rescaled if it had to be
+              if (j == 0 && n > 0) mbar_wait(&bar_ofree[g], (n - 1) & 1, 8);  // O_g still holds the previous work item until read out
+              tcgen05_fence_after();
+              const uint32_t pbase = smem_u32(sP + g * P_BYTES);
+              const uint32_t vbase = smem_u32(sV + st_v * V_BYTES);
+#pragma unroll
+              for (int k = 0; k < KT / 16; ++k) {
+                // A = P (K-major, two 64-key slabs; +32 B per 16 keys inside a swizzle row); B = V (MN-major: +16 key rows * 128 B)
+                const uint64_t dp = desc_kmajor(pbase + (k >> 2) * P_SLAB) + uint64_t((k & 3) * 2);
+                const uint64_t dv = desc_mnmajor(vbase, V_BYTES) + uint64_t(k * 128);
+                umma_f16(tmem_base + 256 + g * 64, dp, dv, p.idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+              }
+              if (g == 1) umma_commit(&kv_empty[st_v]);  // both groups' P V (and, earlier, both S) have consumed this stage
+              umma_commit(&bar_o[g]);
+              ++t[g];
+              if (more) issue_s(g, qb, st_k, s_issued[g]++);
+            }
+            if (++st_v == STAGES) st_v = 0;
+            if (more && ++st_k == STAGES) {
+              st_k = 0;
+              ph_k ^= 1;
+            }
+          }
+          umma_commit(&q_empty[qb]);  // every MMA reading this Q buffer has been issued; it frees when they retire
+        }
+      }
+    }
+  } else {
+    // ============================================================================ softmax
+    setmaxnreg_inc<216>();
+    const int g = wg - 1;                 // query tile of the pair
+    const int lg = warp & 3;              // TMEM lane group of this warp
+    const int row = lg * 32 + lane;
+    const uint32_t lane_off = uint32_t(lg * 32) << 16;
+    const uint32_t tmem_s = tmem_base + g * 128 + lane_off;
+    const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_off;
+    uint8_t* prow = sP + g * P_BYTES + row * 128;
+    const int sw = row & 7;
+    T* obase = static_cast<T*>(p.o);
+    uint32_t t = 0;                       // tiles of this group so far
+    uint32_t n = 0;
+    for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
+      const int pair = int(w % p.n_pairs);
+      const int h = int((w / p.n_pairs) % p.H);
+      const int64_t b = w / (int64_t(p.n_pairs) * p.H);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < p.ntiles; ++j, ++t) {
+        mbar_wait(&bar_s[g], t & 1, 9);
+        tcgen05_fence_after();
+        float s[KT];
+        {
+          uint32_t r0[32], r1[32], r2[32], r3[32];
+          tmem_ld_32x32(tmem_s, r0);
+          tmem_ld_32x32(tmem_s + 32, r1);
+          tmem_ld_32x32(tmem_s + 64, r2);
+          tmem_ld_32x32(tmem_s + 96, r3);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s[i] = __uint_as_float(r0[i]);
+            s[32 + i] = __uint_as_float(r1[i]);
+            s[64 + i] = __uint_as_float(r2[i]);
+            s[96 + i] = __uint_as_float(r3[i]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(&bar_sfree[g]);  // the tensor core may overwrite this S tile
+        const int64_t left = p.Sk - int64_t(j) * KT;
+        if (left < KT) {
+          const int valid = int(left);
+#pragma unroll
+          for (int i = 0; i < KT; ++i)
+            if (i >= valid) s[i] = -INFINITY;
+        }
+        float tmax = fmaxf(s[0], s[1]);
+#pragma unroll
+        for (int i = 2; i < KT; i += 2) tmax = fmaxf(tmax, fmaxf(s[i], s[i + 1]));
+        bool waited_o = false;
+        if (j == 0) {
+          m_run = tmax;  // nothing accumulated yet
+        } else {
+          const float m_new = fmaxf(m_run, tmax);
+          const bool grew = (m_new - m_run) * p.scale_log2e > RESCALE_LOG2;
+          if (__any_sync(0xffffffffu, grew)) {  // TMEM access is warp-collective: the whole warp rescales its 32 rows
+            mbar_wait(&bar_o[g], (t - 1) & 1, 10);  // every P V issued so far has landed in O
+            waited_o = true;
+            tcgen05_fence_after();
+            const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);
+#pragma unroll
+            for (int half = 0; half < HD / 32; ++half) {
+              uint32_t raw[32];
+              tmem_ld_32x32(tmem_o + half * 32, raw);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+              tmem_st_32x32(tmem_o + half * 32, raw);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_run = m_new;
+          }
+        }
+        const float mb = m_run * p.scale_log2e;
+        float psum0 = 0.f, psum1 = 0.f;
+        uint32_t packed[KT / 2];
+#pragma unroll
+        for (int i = 0; i < KT; i += 4) {
+          const float x0 = fmaf(s[i], p.scale_log2e, -mb), x1 = fmaf(s[i + 1], p.scale_log2e, -mb);
+          const float x2 = fmaf(s[i + 2], p.scale_log2e, -mb), x3 = fmaf(s[i + 3], p.scale_log2e, -mb);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2);
+          const float p3 = POLY ? ex2_poly(x3) : ex2_approx(x3);
+          psum0 += p0 + p1;
+          psum1 += p2 + p3;
+          packed[i / 2] = pack2<T>(p0, p1);
+          packed[i / 2 + 1] = pack2<T>(p2, p3);
+        }
+        l_run += psum0 + psum1;
+        // the P buffer of this group was last read by P V of tile t - 1
+        if (j > 0 && !waited_o) mbar_wait(&bar_o[g], (t - 1) & 1, 11);
+        if (j == 0 && t > 0) mbar_wait(&bar_o[g], (t - 1) & 1, 12);  // ... of the previous work item's last tile
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int q = sl * 32 + c * 4;
+            uint4 v = make_uint4(packed[q], packed[q + 1], packed[q + 2], packed[q + 3]);
+            *reinterpret_cast<uint4*>(prow + sl * P_SLAB + ((c ^ sw) << 4)) = v;
+          }
+        }
+        fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
+        tcgen05_fence_before();   // also orders a rescale's tcgen05.st before the MMA that the arrive releases
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[g]);
+      }
+      // ---- read the finished rows out of TMEM
+      mbar_wait(&bar_o[g], (t - 1) & 1, 13);
+      tcgen05_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      float acc[HD];
+#pragma unroll
+      for (int half = 0; half < HD / 32; ++half) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_o + half * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[half * 32 + i] = inv * __uint_as_float(raw[i]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(&bar_ofree[g]);  // the MMA warp may start the next work item's P V
+      const int64_t qi = (int64_t(pair) * 2 + g) * QT + row;
+      if (qi < p.Sq) {
+        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (p.d_out & 7) == 0) {
+#pragma unroll
+          for (int c = 0; c < HD / 8; ++c) {
+            if (c * 8 >= p.d_out) break;
+            uint4 v;
+            v.x = pack2<T>(acc[c * 8], acc[c * 8 + 1]);
+            v.y = pack2<T>(acc[c * 8 + 2], acc[c * 8 + 3]);
+            v.z = pack2<T>(acc[c * 8 + 4], acc[c * 8 + 5]);
+            v.w = pack2<T>(acc[c * 8 + 6], acc[c * 8 + 7]);
+            reinterpret_cast<uint4*>(dst)[c] = v;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < HD; ++i)
+            if (i < p.d_out) dst[i] = from_f<T>(acc[i]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return EncodeTiledFn(nullptr);
+    return reinterpret_cast<EncodeTiledFn>(sym);
+  }();
+  return fn;
+}
+
+// [B, S, H, D] view with strides (sb, ss, D, 1) elements; box = 64 x 1 x 128 rows x 1 (columns >= D are zero filled)
+int make_map(CUtensorMap* map, int dtype, const void* base, int64_t B, int64_t S, int H, int64_t sb, int64_t ss, int D) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) RB200_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t dims[4] = {cuuint64_t(D), cuuint64_t(H), cuuint64_t(S), cuuint64_t(B)};
+  const cuuint64_t strides[3] = {cuuint64_t(D) * 2, cuuint64_t(ss) * 2, cuuint64_t(sb) * 2};
+  const cuuint32_t box[4] = {64, 1, 128, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == RB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult rc = fn(map, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) RB200_FAIL(-4, "sdpa2 tensor map encode failed (%d): S=%lld H=%d ss=%lld sb=%lld", int(rc), (long long)S, H, (long long)ss, (long long)sb);
+  return 0;
+}
+
+bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
+}
+
+template <typename T, bool POLY>
+int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const Attn2Params& prm) {
+  static PerDeviceOnce configured;
+  if (configured.needed()) {
+    if (cudaFuncSetAttribute(tc_sdpa2_kernel<T, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa2: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+    configured.done();
+  }
+  const int64_t cap = sm_count();
+  const int grid = int(prm.total_work < cap ? prm.total_work : cap);
+  tc_sdpa2_kernel<T, POLY><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mq, mk, mv, prm);
+  RB200_CHECK_LAUNCH("tc_sdpa2");
+  return 0;
+}
+
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : fallback;
+}
+
+}  // namespace
+
+// RB200_ATTN_V2: 0 = always the first-generation kernel, 1 (default) = this kernel where it applies.
+// RB200_ATTN_POLY: 1 = every fourth exponential on the FMA pipe (default), 0 = all on MUFU.
+bool tc_sdpa2_supported(const SdpaProblem& p) {
+  static const int enabled = env_int("RB200_ATTN_V2", 1);
+  if (!enabled) return false;
+  if (p.dtype != RB200_BF16 && p.dtype != RB200_FP16) return false;
+  if (p.D < 8 || p.D > 64 || (p.D & 7) != 0 || p.causal) return false;
+  if (p.bias_h != nullptr || (p.k2 != nullptr && p.Sk2 > 0)) return false;
+  if (p.Sq <= QT || p.Sk < 1 || p.B < 1) return false;
+  return ok_operand(p.q, p.q_sb, p.q_ss) && ok_operand(p.k, p.k_sb, p.k_ss) && ok_operand(p.v, p.v_sb, p.v_ss);
+}
+
+int tc_sdpa2(cudaStream_t st, const SdpaProblem& p) {
+  CUtensorMap mq, mk, mv;
+  if (int rc = make_map(&mq, p.dtype, p.q, p.B, p.Sq, p.H, p.q_sb, p.q_ss, p.D)) return rc;
+  if (int rc = make_map(&mk, p.dtype, p.k, p.B, p.Sk, p.H, p.k_sb, p.k_ss, p.D)) return rc;
+  if (int rc = make_map(&mv, p.dtype, p.v, p.B, p.Sk, p.H, p.v_sb, p.v_ss, p.D)) return rc;
+  Attn2Params prm{};
+  prm.o = p.o;
+  prm.o_sb = p.o_sb;
+  prm.o_ss = p.o_ss;
+  prm.H = p.H;
+  prm.Sq = p.Sq;
+  prm.Sk = p.Sk;
+  prm.n_pairs = int(ceil_div(p.Sq, 2 * QT));
+  prm.total_work = int64_t(prm.n_pairs) * p.H * p.B;
+  prm.ntiles = int(ceil_div(p.Sk, KT));
+  prm.scale_log2e = p.scale * 1.4426950408889634f;
+  const uint32_t fmt = p.dtype == RB200_BF16 ? 1u : 0u;
+  const uint32_t common = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(QT >> 4) << 24);
+  prm.idesc_qk = common | (uint32_t(KT >> 3) << 17);                // D = 128 x 128, A and B K-major
+  prm.idesc_pv = common | (uint32_t(HD >> 3) << 17) | (1u << 16);   // D = 128 x 64, B (= V) MN-major
+  prm.d_out = p.D;
+  static const int poly = env_int("RB200_ATTN_POLY", 1);
+  const bool bf = p.dtype == RB200_BF16;
+  if (poly) return bf ? launch<__nv_bfloat16, true>(st, mq, mk, mv, prm) : launch<__half, true>(st, mq, mk, mv, prm);
+  return bf ? launch<__nv_bfloat16, false>(st, mq, mk, mv, prm) : launch<__half, false>(st, mq, mk, mv, prm);
+}
+
+}  // namespace rb200

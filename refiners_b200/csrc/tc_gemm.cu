@@ -721,13 +721,13 @@ int launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, 
                  TcParams& prm) {
   constexpr int MODE = CL;  // template argument: 1 single CTA, 2 multicast pair, 3 cta_group::2 pair
   constexpr int CLUSTER = MODE == 1 ? 1 : 2;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   constexpr size_t SMEM = smem_bytes<BN, MODE>();
   if (MODE == 3) prm.idesc = (prm.idesc & ~(0x1Fu << 24)) | (uint32_t(256 >> 4) << 24);  // UMMA M = 256 across the pair
-  if (!configured) {
+  if (configured.needed()) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<T, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM)) != cudaSuccess)
       RB200_FAIL(-2, "tc_gemm: cannot reserve %zu bytes of shared memory", SMEM);
-    configured = true;
+    configured.done();
   }
   const int64_t groups = int64_t((prm.tiles_m + CLUSTER - 1) / CLUSTER) * prm.tiles_n;
   if (groups > (int64_t(1) << 30)) RB200_FAIL(-1, "tc_gemm: too many tiles");

@@ -5,21 +5,35 @@ registrations per SDXL forward the interpreter would 
 the GPU work.  ``GraphedChain`` runs the walker ONCE under stream capture and replays the
 recorded launch sequence afterwards.
 
-Contexts: while a GraphedChain is attached, ``set_context`` calls on the chain (or on an
-adapter wrapping it) are intercepted: tensor values are copied into static buffers that the
-captured kernels read, so the usual API (``unet.set_timestep(t)`` ...) keeps working and costs a
-device copy instead of a tree walk.  Non-tensor values are compared by equality.
+What a capture bakes in, and how each is kept honest:
 
-The capture is dropped and redone when
-  * the tree is edited anywhere (adapter inject/eject bump the structure epoch),
-  * an input or context value changes shape, dtype or (for non-tensors) value,
-  * ``invalidate()`` is called (do so after replacing parameter storages).
-Python side effects of a forward (residual lists, size stacks) happen at capture time only and
-are undone by ``Chain._reset_context`` as in eager mode.
+  * inputs and TENSOR context values   live in static device buffers; every call copies the current
+                                       values in (CPU tensors too: they are mirrored on the chain's
+                                       device, so a CPU ``timestep`` follows its value instead of being
+                                       frozen into the capture)
+  * non-tensor context values          compared by ``repr``; a change re-captures
+  * the module tree                    ``structure_epoch()``: any edit anywhere (adapter inject / eject,
+                                       append, replace ...) re-captures
+  * Python scalars of modules          ``value_epoch()``: assigning a public int / float / bool / str /
+                                       sequence attribute on any fluxion module (``Multiply.scale``
+                                       behind ``Lora.scale``, ``ip_adapter.scale``, ControlNet /
+                                       ControlLora ``scale`` ...) re-captures - these floats become
+                                       kernel arguments and packed column scales
+  * parameter storage                  a fingerprint of every parameter / buffer (address, version,
+                                       shape, dtype): ``load_state_dict``, ``.to()``, in-place edits
+                                       and swapped ``.weight`` objects re-capture (the eager pack caches
+                                       use the same stamp); writes through ``.data`` are invisible to
+                                       autograd's version counter - call ``invalidate()`` after those.
+
+``set_context`` is observed, not swallowed: the providers keep receiving the values, so an eager call of
+the same chain (debugging, a CPU fallback of the caller) still sees its contexts.  Python side effects
+of a forward (residual lists, size stacks) happen at capture time only and are undone by
+``Chain._reset_context`` as in eager mode.
 """
 
 from __future__ import annotations
 
+import weakref
 from typing import Any
 
 import torch
@@ -27,12 +41,13 @@ from torch import Tensor
 
 from refiners_b200 import backend as B
 from refiners_b200.fluxion.layers import graph as _g
+from refiners_b200.fluxion.layers.base import value_epoch
 from refiners_b200.fluxion.layers.graph import Chain, structure_epoch
 
 
 def _signature(v: Any) -> Any:
     if isinstance(v, Tensor):
-        return ("tensor", tuple(v.shape), v.dtype, str(v.device))
+        return ("tensor", tuple(v.shape), v.dtype)
     return ("value", repr(v))
 
 
@@ -41,47 +56,72 @@ class GraphedChain:
         self.chain = chain
         self.warmup = warmup
         self._graph: torch.cuda.CUDAGraph | None = None
-        self._epoch = -1
+        self._epochs: tuple[int, int] = (-1, -1)
         self._pending: dict[tuple[int, str], dict[str, Any]] = {}   # (id(owner), context) -> values
         self._owners: dict[int, Chain] = {}
         self._static: dict[tuple[int, str, str], Tensor] = {}
         self._static_in: list[Tensor] = []
         self._static_out: Any = None
         self._sig: Any = None
+        self._tensors: list[Tensor] = []
+        self._fingerprint: Any = None
         self._applying = False
         self.launches_per_replay = 0
         self.captures = 0
         self.replays = 0
-        _g._context_listeners.append(self._on_set_context)
+        # the module-global listener list must not keep this runner (and, through it, the model and its
+        # device memory) alive: it holds a weak reference and unregisters itself once the runner is gone
+        ref = weakref.ref(self)
+
+        def listener(owner: Chain, context: str, value: Any) -> bool:
+            me = ref()
+            if me is None:
+                if listener in _g._context_listeners:
+                    _g._context_listeners.remove(listener)
+                return False
+            me._observe(owner, context, value)
+            return False  # never consumed: the provider is updated as usual
+
+        self._listener = listener
+        _g._context_listeners.append(listener)
 
     def close(self) -> None:
-        if self._on_set_context in _g._context_listeners:
-            _g._context_listeners.remove(self._on_set_context)
+        if self._listener in _g._context_listeners:
+            _g._context_listeners.remove(self._listener)
         self._graph = None
+        self._static.clear()
+        self._static_in = []
+        self._static_out = None
 
     def invalidate(self) -> None:
         self._graph = None
 
-    # -- context interception -----------------------------------------------------------------
-    def _on_set_context(self, owner: Chain, context: str, value: Any) -> bool:
+    # -- context observation ------------------------------------------------------------------
+    def _observe(self, owner: Chain, context: str, value: Any) -> None:
         if self._applying or not isinstance(value, dict):
-            return False
+            return
         if owner is not self.chain and owner not in self.chain.get_parents():
-            return False
+            return
         self._owners[id(owner)] = owner
         self._pending.setdefault((id(owner), context), {}).update(value)
-        return True
 
-    def _apply_contexts(self, use_static: bool) -> None:
-        """Push the recorded context values (or their static mirrors) through the real API."""
+    def _apply_contexts(self) -> None:
+        """Hand the static mirrors of the recorded tensor values (and the other values as they are) to the
+        real providers, so that the walker under capture reads the buffers the replays will refresh."""
         self._applying = True
         try:
             for (oid, context), values in self._pending.items():
-                payload = {
-                    key: (self._static[(oid, context, key)] if use_static and isinstance(v, Tensor) and v.is_cuda else v)
-                    for key, v in values.items()
-                }
+                payload = {key: (self._static[(oid, context, key)] if isinstance(v, Tensor) else v) for key, v in values.items()}
                 self._owners[oid].set_context(context, payload)
+        finally:
+            self._applying = False
+
+    def _restore_contexts(self) -> None:
+        """After a capture: give the providers the caller's own values back."""
+        self._applying = True
+        try:
+            for (oid, context), values in self._pending.items():
+                self._owners[oid].set_context(context, dict(values))
         finally:
             self._applying = False
 
@@ -91,36 +131,49 @@ class GraphedChain:
             for (oid, context), values in sorted(self._pending.items(), key=lambda kv: (kv[0][0], kv[0][1]))
             for key, v in sorted(values.items())
         )
-        return (tuple(_signature(t) for t in inputs), ctx)
+        return (tuple((_signature(t), str(t.device)) for t in inputs), ctx)
+
+    def _stamp(self) -> Any:
+        return tuple((t.data_ptr(), t._version) for t in self._tensors)
 
     def _capture(self, inputs: tuple[Tensor, ...]) -> None:
+        device = inputs[0].device
         self._static_in = [t.clone() for t in inputs]
         self._static = {
-            (oid, context, key): v.clone()
+            (oid, context, key): v.detach().to(device, copy=True)
             for (oid, context), values in self._pending.items()
             for key, v in values.items()
-            if isinstance(v, Tensor) and v.is_cuda
+            if isinstance(v, Tensor)
         }
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):  # warm-up off the capture: packs weights, sizes the allocator
             for _ in range(self.warmup):
-                self._apply_contexts(use_static=True)
+                self._apply_contexts()
                 self.chain(*self._static_in)
-        torch.cuda.current_stream().wait_stream(side)
-        self._apply_contexts(use_static=True)
+        torch.cuda.current_stream(device).wait_stream(side)
+        self._apply_contexts()
         graph = torch.cuda.CUDAGraph()
         before = B.launch_count()
         with torch.cuda.graph(graph):
             self._static_out = self.chain(*self._static_in)
         self.launches_per_replay = B.launch_count() - before
+        self._restore_contexts()
         self._graph = graph
-        self._epoch = structure_epoch()
+        self._epochs = (structure_epoch(), value_epoch())
+        self._tensors = [*self.chain.parameters(), *self.chain.buffers()]
+        self._fingerprint = self._stamp()
         self.captures += 1
 
     def __call__(self, *inputs: Tensor) -> Any:
         sig = self._signature(inputs)
-        if self._graph is None or self._epoch != structure_epoch() or sig != self._sig:
+        stale = (
+            self._graph is None
+            or self._epochs != (structure_epoch(), value_epoch())
+            or sig != self._sig
+            or self._fingerprint != self._stamp()
+        )
+        if stale:
             self._capture(inputs)
             self._sig = sig
         else:
@@ -128,7 +181,7 @@ class GraphedChain:
                 buf.copy_(new, non_blocking=True)
             for (oid, context), values in self._pending.items():
                 for key, v in values.items():
-                    if isinstance(v, Tensor) and v.is_cuda:
+                    if isinstance(v, Tensor):
                         self._static[(oid, context, key)].copy_(v, non_blocking=True)
         assert self._graph is not None
         self._graph.replay()

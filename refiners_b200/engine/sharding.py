@@ -36,16 +36,36 @@ def shard_cfg_batch(x: Tensor, rank: int, world: int) -> Tensor:
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> int:
-    """Make every rank's parameters and buffers identical to ``src``'s; returns bytes sent."""
+    """Make every rank's parameters and buffers identical to ``src``'s; returns bytes sent.
+    The tensors are overwritten in place under ``no_grad`` (their version counters move, so stamped
+    caches notice) and every packed-weight cache of the backend is dropped: a forward that ran before
+    the broadcast must not leave packs of the old values behind."""
     sent = 0
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src)
-        sent += t.numel() * t.element_size()
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            received = t.detach().clone()
+            dist.broadcast(received, src=src)
+            t.copy_(received)
+            sent += t.numel() * t.element_size()
+    from refiners_b200 import backend
+
+    backend.clear_caches()
     return sent
 
 
-def gather_batch(x: Tensor, world: int) -> Tensor:
-    """All-gather equally sized per-rank results along the batch (end of a run, off the hot path)."""
-    parts = [torch.empty_like(x) for _ in range(world)]
-    dist.all_gather(parts, x.contiguous())
-    return torch.cat(parts)
+def gather_batch(x: Tensor, world: int, total: int | None = None) -> Tensor:
+    """All-gather per-rank results along the batch (end of a run, off the hot path).  ``shard_range``
+    spreads a remainder over the first ranks, so shards may differ by one row: every rank pads to the
+    largest shard and the padding is cut after the gather.  ``total`` is the unsharded batch size
+    (default: ``world`` equal shards)."""
+    rank = dist.get_rank()
+    total = x.shape[0] * world if total is None else total
+    sizes = [hi - lo for lo, hi in (shard_range(total, r, world) for r in range(world))]
+    assert x.shape[0] == sizes[rank], f"rank {rank} holds {x.shape[0]} rows, its shard of {total} has {sizes[rank]}"
+    widest = max(sizes)
+    padded = x.contiguous()
+    if padded.shape[0] < widest:
+        padded = torch.cat((padded, padded.new_zeros((widest - padded.shape[0], *padded.shape[1:]))))
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    return torch.cat([part[:n] for part, n in zip(parts, sizes)])

@@ -25,6 +25,16 @@ if TYPE_CHECKING:
 
 T = TypeVar("T", bound="Module")
 _BASIC = (str, float, int, bool)
+_PLAIN = (float, int, bool, str, list, tuple)
+
+# Bumped whenever a public plain-Python attribute (a scale, an eps, a flag ...) is assigned on any fluxion
+# module.  Such values end up as kernel arguments and inside packed weights; a captured CUDA graph
+# (refiners_b200.engine.graph) compares this counter to know that its baked-in copies are stale.
+_value_epoch = 0
+
+
+def value_epoch() -> int:
+    return _value_epoch
 
 
 def _is_basic(value: Any) -> bool:
@@ -40,6 +50,12 @@ class Module(torch.nn.Module):
 
     def __init__(self, *args: Any, **kwargs: Any) -> None:
         super().__init__(*args, **kwargs)
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        if isinstance(value, _PLAIN) and name[:1] != "_":
+            global _value_epoch
+            _value_epoch += 1
+        super().__setattr__(name, value)
 
     def load_from_safetensors(self: T, tensors_path: str | Path, strict: bool = True) -> T:
         self.load_state_dict(load_from_safetensors(tensors_path), strict=strict)

@@ -86,7 +86,8 @@ class RangeAdapter2d(fl.Sum, Adapter[fl.Conv2d]):
             children = list(self)
             if len(children) == 2 and type(children[0]) is fl.Conv2d and isinstance(children[1], fl.Chain):
                 conv, side = children
-                no_hooks = not (conv._forward_hooks or conv._forward_pre_hooks)
+                hooked = [conv, side, *side]
+                no_hooks = not any(m._forward_hooks or m._forward_pre_hooks for m in hooked)
                 if no_hooks and B.conv_supported(conv) and len(side) == 4 and type(side[3]) is fl.Reshape:
                     # side chain: UseContext -> SiLU -> Linear -> Reshape(C,1,1); run all but the reshape
                     bias = inputs[0]

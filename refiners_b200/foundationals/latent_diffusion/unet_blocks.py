@@ -49,7 +49,7 @@ class ResidualBlock(fl.Sum):
         spliced after the last conv - takes the generic Sum path."""
         if len(inputs) == 1 and isinstance(inputs[0], Tensor) and inputs[0].is_cuda and B.fusion_enabled() and len(self) == 2:
             body, shortcut = self[0], self[1]
-            if type(body) is fl.Chain and body._steps()[-1][0] == "call":
+            if type(body) is fl.Chain and body._steps()[-1][0] == "call" and not fusion._hooked(body, shortcut):
                 last = fusion.tail_conv(body)
                 if last is not None:
                     skip = shortcut(*inputs)

@@ -302,6 +302,12 @@ SDPA_CASES = [
     (1, 5, 260, 77, 40),
     (2, 3, 128, 4, 64),      # IP-Adapter token count
     (1, 1, 1, 1, 64),
+    # second-generation kernel (tc_attention2.cu: Sq > 128, d <= 64): ragged query pairs, partial key tiles
+    (1, 2, 257, 129, 64),    # 3 query tiles -> 2 pairs (phantom fourth tile), 2 key tiles with 1 valid key in the last
+    (2, 3, 300, 255, 64),
+    (1, 4, 512, 640, 40),    # zero-filled head columns, 5 key tiles
+    (3, 60, 384, 300, 64),   # 360 work items: several per persistent CTA (Q double buffer, O hand-over between items)
+    (1, 2, 130, 1, 8),
 ]
 
 
@@ -466,3 +472,154 @@ def test_packed_weight_cache_is_not_fooled_by_address_reuse(cuda_device):
         del w
     for o, r in zip(outs, refs):
         assert_close(o, r, torch.bfloat16, what="conv after weight replacement")
+
+
+# ------------------------------------------------------------------------------ production shapes
+# The shapes the benchmark actually runs (SURVEY.md section 8a at UNet batch 16): 64 key tiles of online softmax,
+# pair-mode GEMMs with multi-wave tails, 128^2 / 32^2 convolutions.  The reference is the same op in fp32 torch
+# evaluated on the GPU (TF32 off) from the rounded operands - the CPU would need minutes for these.
+def _fp32_reference_mode():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+BIG_SDPA = [
+    # (B, H, Sq, Sk, D)
+    (16, 20, 1024, 1024, 64),   # SDXL self-attention, 1280-wide blocks
+    (4, 10, 4096, 4096, 64),    # SDXL self-attention, 640-wide blocks (64 key tiles)
+    (16, 20, 1024, 77, 64),     # text cross-attention
+    (4, 10, 4096, 77, 64),
+    (2, 16, 4096, 4096, 80),    # SAM global attention geometry without the bias term
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("case", BIG_SDPA, ids=str)
+def test_sdpa_production_shapes(cuda_device, dtype, case):
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    Bn, H, Sq, Sk, D = case
+    dev = lambda t: t.to(cuda_device, dtype)
+    q, k, v = dev(_gen((Bn, Sq, H * D), 170)), dev(_gen((Bn, Sk, H * D), 171)), dev(_gen((Bn, Sk, H * D), 172))
+    with torch.no_grad():
+        y = B.sdpa(q, k, v, H)
+        ref = torch.cat([_sdpa_ref(q[i : i + 1].float(), k[i : i + 1].float(), v[i : i + 1].float(), H) for i in range(Bn)])
+    assert_close(y, ref, dtype, scale=4.0, what=f"sdpa{case}")
+
+
+BIG_LINEAR = [
+    # (M, K, N, residual)
+    (16384, 1280, 1280, True),    # attention out-projection + residual: 4.3 waves of 256-wide tiles
+    (16384, 1280, 3840, False),   # fused q/k/v
+    (16384, 5120, 1280, True),    # GEGLU down-projection
+    (65536, 640, 640, True),
+    (65536, 640, 1920, False),
+    (1232, 2048, 2560, False),    # text K/V projection
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("case", BIG_LINEAR, ids=str)
+def test_linear_production_shapes(cuda_device, dtype, case):
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    M, K, N, with_res = case
+    dev = lambda t: t.to(cuda_device, dtype)
+    x, w, b = dev(_gen((M, K), 180)), dev(_gen((N, K), 181, K**-0.5)), dev(_gen((N,), 182))
+    r = dev(_gen((M, N), 183)) if with_res else None
+    with torch.no_grad():
+        y = B.linear(x, w, b, residual=r)
+        ref = F.linear(x.float(), w.float(), b.float())
+        if r is not None:
+            ref = ref + r.float()
+    assert_close(y, ref, dtype, what=f"linear{case}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16], ids=str)
+def test_linear_geglu_production_shape(cuda_device, dtype):
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    M, K, Fh = 16384, 1280, 5120
+    dev = lambda t: t.to(cuda_device, dtype)
+    x, w, b = dev(_gen((M, K), 184)), dev(_gen((2 * Fh, K), 185, K**-0.5)), dev(_gen((2 * Fh,), 186))
+    with torch.no_grad():
+        y = B.linear_geglu(x, w, b)
+        a, g = F.linear(x.float(), w.float(), b.float()).chunk(2, dim=-1)
+        ref = a * F.gelu(g)
+    assert_close(y, ref, dtype, scale=2.0, what="geglu 16384x1280->5120")
+
+
+BIG_CONV = [
+    # (B, Cin, Cout, H, W, k, stride, pad)
+    (16, 1280, 1280, 32, 32, 3, 1, 1),
+    (16, 320, 320, 128, 128, 3, 1, 1),
+    (16, 640, 640, 64, 64, 3, 2, 1),     # Downsample
+    (16, 1920, 640, 64, 64, 1, 1, 0),    # shortcut of an up block
+    (4, 4, 320, 128, 128, 3, 1, 1),      # latent input conv (zero-extended channels)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("case", BIG_CONV, ids=str)
+def test_conv2d_production_shapes(cuda_device, dtype, case):
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    Bn, Cin, Cout, H, W, k, stride, pad = case
+    dev = lambda t: t.to(cuda_device, dtype)
+    x = dev(_gen((Bn, Cin, H, W), 190)).contiguous(memory_format=torch.channels_last)
+    w, b = dev(_gen((Cout, Cin, k, k), 191, (Cin * k * k) ** -0.5)), dev(_gen((Cout,), 192))
+    with torch.no_grad():
+        y = B.conv2d(x, w, b, stride, pad)
+        ref = F.conv2d(x.float(), w.float(), b.float(), stride=stride, padding=pad)
+    assert_close(y, ref, dtype, what=f"conv{case}")
+
+
+@pytest.mark.parametrize("shape", [(16, 320, 128, 128), (16, 1280, 32, 32), (16, 2560, 32, 32)], ids=str)
+def test_group_norm_silu_production_shapes(cuda_device, shape):
+    from refiners_b200 import backend as B
+
+    dtype = torch.bfloat16
+    dev = lambda t: t.to(cuda_device, dtype)
+    x = dev(_gen(shape, 193, 2.0) + 0.5).contiguous(memory_format=torch.channels_last)
+    g, b = dev(1 + 0.1 * _gen((shape[1],), 194)), dev(0.1 * _gen((shape[1],), 195))
+    with torch.no_grad():
+        y = B.group_norm(x, 32, g, b, 1e-5, silu=True)
+        ref = F.silu(F.group_norm(x.float(), 32, g.float(), b.float(), 1e-5))
+    assert_close(y, ref, dtype, scale=2.0, what=f"gn+silu{shape}")
+
+
+@pytest.mark.parametrize("shape", [(16, 1024, 1280), (16, 4096, 640)], ids=str)
+def test_layer_norm_production_shapes(cuda_device, shape):
+    from refiners_b200 import backend as B
+
+    dtype = torch.bfloat16
+    dev = lambda t: t.to(cuda_device, dtype)
+    x, g, b = dev(_gen(shape, 196, 3.0)), dev(1 + 0.1 * _gen((shape[-1],), 197)), dev(0.1 * _gen((shape[-1],), 198))
+    with torch.no_grad():
+        y = B.layer_norm(x, g, b, 1e-5)
+        ref = F.layer_norm(x.float(), (shape[-1],), g.float(), b.float(), 1e-5)
+    assert_close(y, ref, dtype, scale=2.0, what=f"ln{shape}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("shape", [(2, 4, 512, 1024), (1, 2, 300, 700)], ids=str)
+def test_sdpa_growing_maxima(cuda_device, dtype, shape):
+    """The second-generation attention kernel keeps a STALE running maximum and rescales the TMEM-resident output only
+    when a row's maximum grows by more than 2^8: keys whose magnitude ramps up along the sequence make every later key
+    tile raise the maximum by a wide margin (the rescale path), while a flat first half exercises the stale path."""
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    Bn, H, Sq, Sk = shape
+    D = 64
+    ramp = torch.linspace(0.5, 6.0, Sk).reshape(1, Sk, 1)
+    dev = lambda t: t.to(cuda_device, dtype)
+    q, k, v = dev(_gen((Bn, Sq, H * D), 270) * 2.0), dev(_gen((Bn, Sk, H * D), 271) * ramp), dev(_gen((Bn, Sk, H * D), 272))
+    with torch.no_grad():
+        y = B.sdpa(q, k, v, H)
+        ref = _sdpa_ref(q.float(), k.float(), v.float(), H)
+    assert_close(y, ref, dtype, scale=4.0, what=f"sdpa growing maxima {shape}")
