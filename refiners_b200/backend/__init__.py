@@ -29,6 +29,10 @@ _UNARY = {"silu": 0, "gelu": 1, "gelu_tanh": 2, "gelu_sigmoid": 3, "relu": 4, "s
 EPI_NONE, EPI_GEGLU, EPI_GELU, EPI_SILU = 0, 1, 2, 3
 
 _fusion = os.environ.get("RB200_FUSION", "1") != "0"
+# LoRA-adapted Linears: 1 (default) = fold the rank terms into a cached effective weight W + sum_i s_i B_i A_i (one GEMM
+# launch per adapted layer, re-merged when a factor or a scale changes); 0 = keep them separate (rank-space GEMM + base
+# GEMM with the up-projection as extra k-blocks, two launches)
+_lora_merge = os.environ.get("RB200_LORA_MERGE", "1") != "0"
 
 
 class BackendError(RuntimeError):
@@ -42,6 +46,16 @@ def fusion_enabled() -> bool:
 def set_fusion(enabled: bool) -> bool:
     global _fusion
     previous, _fusion = _fusion, bool(enabled)
+    return previous
+
+
+def lora_merge_enabled() -> bool:
+    return _lora_merge
+
+
+def set_lora_merge(enabled: bool) -> bool:
+    global _lora_merge
+    previous, _lora_merge = _lora_merge, bool(enabled)
     return previous
 
 
@@ -214,10 +228,11 @@ _patch_cache = _PackCache()
 _geglu_cache = _PackCache()
 _lora_cache = _PackCache()
 _concat_cache = _PackCache()
+_merge_cache = _PackCache()
 
 
 def clear_caches() -> None:
-    for cache in (_conv_cache, _conv_pad_cache, _patch_cache, _geglu_cache, _lora_cache, _concat_cache):
+    for cache in (_conv_cache, _conv_pad_cache, _patch_cache, _geglu_cache, _lora_cache, _concat_cache, _merge_cache):
         cache.clear()
 
 
@@ -717,6 +732,39 @@ def pack_loras(x: Tensor, w: Tensor, loras: Sequence[tuple[Tensor, Tensor, float
     return _lora_cache.put(key, sources, (down_cat, up_cat, colscale))
 
 
+def merged_lora_weight(weight: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> Tensor:
+    """``W + sum_i s_i B_i A_i`` ([N, K], the dtype of W), cached per (W, factors, scales).
+
+    The scales and factors of a LoRA are step-invariant, so the adapted layer
+    ``x W^T + sum_i s_i (x A_i^T) B_i^T`` (fluxion/adapters/lora.py:383-448 of the reference) is evaluated as ONE GEMM
+    against the merged weight.  The merge itself is one launch of the library's GEMM: rows of ``[s_i B_i]`` times
+    ``[A_i]^T`` with W as the epilogue residual, accumulated in fp32 and rounded once to the weight dtype - the same
+    single rounding every weight of the model has already been through."""
+    sources = [weight] + [t for d, u, _ in loras for t in (d, u)]
+    key = _PackCache.key(*sources) + tuple(float(s) for _, _, s in loras)
+    hit = _merge_cache.get(key, sources)
+    if hit is not None:
+        return hit
+    N, K = weight.shape
+    for i, (d, u, _) in enumerate(loras):
+        if d.shape[1] != K or u.shape[0] != N or u.shape[1] != d.shape[0]:
+            raise BackendError(f"LoRA {i}: down{tuple(d.shape)} / up{tuple(u.shape)} do not fit Linear({K}->{N})")
+        _same(weight, d, u)
+    total = sum(d.shape[0] for d, _, _ in loras)
+    r_pad = (total + 15) // 16 * 16
+    up_scaled = weight.new_zeros((N, r_pad))
+    down_t = weight.new_zeros((K, r_pad))
+    at = 0
+    for d, u, s in loras:  # one-time packing glue (a few MB); the product below is the library's own GEMM
+        r = d.shape[0]
+        up_scaled[:, at : at + r] = u.detach() * float(s)
+        down_t[:, at : at + r] = d.detach().t()
+        at += r
+    w = weight.detach()
+    merged = _ops.linear(up_scaled, down_t, None, w if w.stride(-1) == 1 else w.contiguous(), None, None, None, EPI_NONE)
+    return _merge_cache.put(key, sources, merged)
+
+
 def lora_fusable(x: Tensor, loras: Sequence[tuple[Tensor, Tensor, float]]) -> bool:
     return len(loras) > 0 and all(d.is_cuda and u.is_cuda and d.dtype == x.dtype for d, u, _ in loras)
 
@@ -733,7 +781,10 @@ def linear(
     _inference_only(x, weight, bias)
     down = up = scale = None
     if loras:
-        down, up, scale = pack_loras(x, weight, loras)
+        if _lora_merge:
+            weight = merged_lora_weight(weight, loras)
+        else:
+            down, up, scale = pack_loras(x, weight, loras)
     return _ops.linear(x, weight, bias, residual, down, up, scale, epilogue)
 
 

@@ -33,6 +33,32 @@ def _hooked(*modules: Any) -> bool:
     return any(m._forward_hooks or m._forward_pre_hooks for m in modules)
 
 
+def _linear_like(layer: Any) -> bool:
+    """A plain Linear, or a LoraAdapter standing where a Linear stood (the adapter may be evaluated as one GEMM against
+    the merged weight, see ``linear_params``)."""
+    from refiners_b200.fluxion.adapters.lora import LoraAdapter
+    from refiners_b200.fluxion.layers.leaves import Linear
+
+    return type(layer) is Linear or type(layer) is LoraAdapter
+
+
+def linear_params(layer: Any) -> tuple[Tensor, Tensor | None, int, int] | None:
+    """(weight, bias, in_features, out_features) with which ``layer`` can be evaluated as ONE plain GEMM right now, or None.
+    A hook-free Linear: its own parameters.  A hook-free LoraAdapter around a Linear whose LoRAs are all plain LinearLoras
+    (and with LoRA merging enabled): the cached merged weight ``W + sum_i s_i B_i A_i`` (backend.merged_lora_weight)."""
+    from refiners_b200.fluxion.adapters.lora import LoraAdapter
+    from refiners_b200.fluxion.layers.leaves import Linear
+
+    if type(layer) is Linear:
+        return None if _hooked(layer) else (layer.weight, layer.bias, layer.in_features, layer.out_features)
+    if type(layer) is LoraAdapter and B.lora_merge_enabled() and not _hooked(layer):
+        triples = layer._fusable()  # None unless the children are [hook-free Linear, hook-free plain LinearLoras...]
+        base = layer[0]
+        if triples is not None and base.weight.is_cuda and all(d.is_cuda and u.is_cuda and d.dtype == base.weight.dtype for d, u, _ in triples):
+            return B.merged_lora_weight(base.weight, triples), base.bias, base.in_features, base.out_features
+    return None
+
+
 def build_plan(chain: Any) -> list[tuple[Any, ...]]:
     from refiners_b200.fluxion.layers.leaves import GLU, GeLU, GeLUApproximation, GroupNorm, Linear, SiLU
 
@@ -46,14 +72,14 @@ def build_plan(chain: Any) -> list[tuple[Any, ...]]:
             plan.append(("gn_silu", name, layer, nxt))
             i += 2
         elif (
-            type(layer) is Linear
+            _linear_like(layer)
             and type(nxt) is GLU
             and type(nxt.activation) is GeLU
             and nxt.activation.approximation is GeLUApproximation.NONE
         ):
             plan.append(("linear_geglu", name, layer, nxt))
             i += 2
-        elif type(layer) is Linear and (
+        elif _linear_like(layer) and (
             type(nxt) is SiLU or (type(nxt) is GeLU and nxt.approximation is GeLUApproximation.NONE)
         ):
             plan.append(("linear_act", name, layer, nxt, B.EPI_SILU if type(nxt) is SiLU else B.EPI_GELU))
@@ -81,14 +107,14 @@ def run_steps(chain: Any, steps: list[tuple[Any, ...]], args: tuple[Any, ...]) -
             kind == "linear_geglu"
             and fuse
             and _cuda_tensor(args)
-            and not _hooked(step[2], step[3], step[3].activation)
-            and B.geglu_fusable(step[2].weight)
+            and not _hooked(step[3], step[3].activation)
+            and (prm := linear_params(step[2])) is not None
+            and B.geglu_fusable(prm[0])
         ):
-            lin = step[2]
-            result = chain._call_fused(step[1], lambda x, lin=lin: B.linear_geglu(x, lin.weight, lin.bias), *args)
-        elif kind == "linear_act" and fuse and _cuda_tensor(args) and not _hooked(step[2], step[3]):
-            lin, epi = step[2], step[4]
-            result = chain._call_fused(step[1], lambda x, lin=lin, epi=epi: B.linear(x, lin.weight, lin.bias, epilogue=epi), *args)
+            result = chain._call_fused(step[1], lambda x, prm=prm: B.linear_geglu(x, prm[0], prm[1]), *args)
+        elif kind == "linear_act" and fuse and _cuda_tensor(args) and not _hooked(step[3]) and (prm := linear_params(step[2])) is not None:
+            epi = step[4]
+            result = chain._call_fused(step[1], lambda x, prm=prm, epi=epi: B.linear(x, prm[0], prm[1], epilogue=epi), *args)
         elif kind == "call":
             result = chain._call_layer(step[2], step[1], *args)
         else:  # unfused pair
@@ -157,10 +183,10 @@ def forward_with_residual(chain: Any, args: tuple[Any, ...], residual: Tensor) -
         name, last = steps[-1][1], steps[-1][2]
         h = run_steps(chain, steps[:-1], args) if len(steps) > 1 else (args[0] if len(args) == 1 else args)
         hargs = h if isinstance(h, tuple) else (h,)
-        if type(last) is Linear and not _hooked(last) and len(hargs) == 1 and isinstance(hargs[0], Tensor):
+        if _linear_like(last) and len(hargs) == 1 and isinstance(hargs[0], Tensor) and (prm := linear_params(last)) is not None:
             t = hargs[0]
-            if t.is_cuda and t.shape[:-1] == residual.shape[:-1] and last.out_features == residual.shape[-1] and t.dtype == residual.dtype:
-                fused = chain._call_fused(name, lambda u: B.linear(u, last.weight, last.bias, residual=residual), t)
+            if t.is_cuda and t.shape[:-1] == residual.shape[:-1] and prm[3] == residual.shape[-1] and t.dtype == residual.dtype:
+                fused = chain._call_fused(name, lambda u: B.linear(u, prm[0], prm[1], residual=residual), t)
         elif isinstance(last, Chain) and type(last).forward is Chain.forward and not _hooked(last):
             fused = chain._call_fused(name, lambda *u: forward_with_residual(last, u, residual), *hargs)
         elif hasattr(last, "_forward_with_residual") and not _hooked(last):
@@ -199,20 +225,23 @@ def try_fuse_distribute(chain: Any, args: tuple[Any, ...]) -> Any:
     if len(items) != len(args) or len(items) < 2:
         return NotImplemented
     n = len(items)
+    if not any(_linear_like(m) for _, m in items):
+        return NotImplemented
+    # (weight, bias, in, out) of every child that is one plain GEMM right now (a Linear, or a LoraAdapter with merged weight)
+    params = [linear_params(m) if _linear_like(m) and isinstance(a, Tensor) and a.is_cuda else None for (_, m), a in zip(items, args)]
     runs: list[tuple[int, int]] = []
     i = 0
     while i < n:
         j = i + 1
-        lin = items[i][1]
-        if type(lin) is Linear and isinstance(args[i], Tensor) and args[i].is_cuda and not _hooked(lin):
+        first = params[i]
+        if first is not None:
             while (
                 j < n
-                and type(items[j][1]) is Linear
-                and not _hooked(items[j][1])
+                and params[j] is not None
                 and _same_tensor(args[i], args[j])
-                and items[j][1].in_features == lin.in_features
-                and (items[j][1].bias is None) == (lin.bias is None)
-                and items[j][1].weight.dtype == lin.weight.dtype
+                and params[j][2] == first[2]
+                and (params[j][1] is None) == (first[1] is None)
+                and params[j][0].dtype == first[0].dtype
             ):
                 j += 1
         runs.append((i, j))
@@ -224,11 +253,11 @@ def try_fuse_distribute(chain: Any, args: tuple[Any, ...]) -> Any:
         if j - i == 1:
             outs[i] = chain._call_layer(items[i][1], items[i][0], args[i])
             continue
-        group = [items[k][1] for k in range(i, j)]
-        w, b = B.concat_linear_weights([m.weight for m in group], [m.bias for m in group])
+        group = params[i:j]
+        w, b = B.concat_linear_weights([g[0] for g in group], [g[1] for g in group])
         y = chain._call_fused(items[i][0], lambda x, w=w, b=b: B.linear(x, w, b), args[i])
         off = 0
-        for k, m in zip(range(i, j), group):
-            outs[k] = y[..., off : off + m.out_features]
-            off += m.out_features
+        for k, g in zip(range(i, j), group):
+            outs[k] = y[..., off : off + g[3]]
+            off += g[3]
     return tuple(outs)

@@ -104,8 +104,11 @@ def test_linear_geglu(cuda_device, kernel_mode, dtype, shape):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=str)
 @pytest.mark.parametrize("ranks", [(16,), (16, 16), (4, 8, 32)], ids=str)
-def test_linear_lora(cuda_device, kernel_mode, dtype, ranks):
-    """y = x W^T + b + sum_i s_i (x A_i^T) B_i^T (lora.py:383-448 in the reference), fp32 math."""
+@pytest.mark.parametrize("merge", [True, False], ids=["merged", "two-launch"])
+def test_linear_lora(cuda_device, kernel_mode, dtype, ranks, merge):
+    """y = x W^T + b + sum_i s_i (x A_i^T) B_i^T (lora.py:383-448 in the reference), fp32 math.  Both evaluations:
+    one GEMM against the cached merged weight W + sum_i s_i B_i A_i (default), and rank-space GEMM + base GEMM with the
+    up-projection as extra k-blocks."""
     from refiners_b200 import backend as B
 
     M, K, N = 500, 320, 640
@@ -116,10 +119,22 @@ def test_linear_lora(cuda_device, kernel_mode, dtype, ranks):
         down, up, s = _gen((r, K), 20 + i, 1 / r), _gen((N, r), 30 + i, 0.05), 0.5 + 0.7 * i
         ref = ref + s * F.linear(F.linear(rounded(x, dtype), rounded(down, dtype)), rounded(up, dtype))
         loras.append((down.to(cuda_device, dtype), up.to(cuda_device, dtype), s))
-    with torch.no_grad():
-        y = B.linear(x.to(cuda_device, dtype), w.to(cuda_device, dtype), b.to(cuda_device, dtype), loras=loras)
-    # the rank-space intermediate is rounded to the activation dtype once: allow 3 eps
+    prev = B.set_lora_merge(merge)
+    try:
+        with torch.no_grad():
+            wd = w.to(cuda_device, dtype)
+            before = B.launch_count()
+            y = B.linear(x.to(cuda_device, dtype), wd, b.to(cuda_device, dtype), loras=loras)
+            first = B.launch_count() - before
+            before = B.launch_count()
+            y2 = B.linear(x.to(cuda_device, dtype), wd, b.to(cuda_device, dtype), loras=loras)
+            again = B.launch_count() - before
+    finally:
+        B.set_lora_merge(prev)
+    # the rank-space intermediate (two-launch) / the merged weight (merged) is rounded to the operand dtype once: 3 eps
     assert_close(y, ref, dtype, scale=3.0, what=f"lora{ranks}")
+    assert torch.equal(y, y2)
+    assert again == (1 if merge else 2), f"{again} launches per adapted Linear (first call: {first})"
 
 
 CONV_CASES = [

@@ -159,20 +159,24 @@ def test_ip_adapter_gpu(cuda_device, dtype, fusion):
         B.set_fusion(prev)
 
 
-def make_lora_block():
+def make_lora_block(oracle_loras: dict | None = None):
+    """``oracle_loras`` (optional) receives {original path of the adapted Linear: [(down, up, scale), ...]} - the
+    description oracle.unet.Weights wants."""
     torch.manual_seed(3)
     ca = CrossAttentionBlock2d(64, context_embedding_dim=48, context_key="ctx", num_attention_heads=1, num_attention_layers=1,
                                use_bias=False, use_linear_projection=True)
     top = fl.Chain(ca)
     plain_sd = {k: v.clone() for k, v in top.state_dict().items()}
+    paths = {id(m): name for name, m in top.named_modules()}
     targets = [(m, p) for m, p in top.walk(fl.Linear, recurse=True) if "CrossAttentionBlock" in {type(a).__name__ for a in p.get_parents() + [p]}]
-    merged = dict(plain_sd)
     for i, (lin, parent) in enumerate(targets):
         loras = []
         for j, (rank, scale) in enumerate(((4, 1.0), (8, 1.4))):
             lora = LinearLora(f"l{j}", in_features=lin.in_features, out_features=lin.out_features, rank=rank, scale=scale)
             lora.up.weight.data.normal_(0, 0.05)
             loras.append(lora)
+            if oracle_loras is not None:
+                oracle_loras.setdefault(paths[id(lin)], []).append((lora.down.weight.detach().clone(), lora.up.weight.detach().clone(), scale))
         LoraAdapter(lin, *loras).inject(parent)
     return top, ca, plain_sd
 
@@ -202,19 +206,38 @@ def test_lora_injection_matches_merged_weights_host():
         check(y, merged_top(x), "host")
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
-@pytest.mark.parametrize("fusion", [True, False], ids=["fused", "unfused"])
-def test_lora_block_gpu(cuda_device, dtype, fusion):
-    from refiners_b200 import backend as B
+def test_lora_block_oracle_host():
+    """The host mirror of a LoRA-adapted block against the ORACLE restatement (oracle.unet with Weights.loras)."""
+    from oracle import unet as ounet
 
-    top, ca, _ = make_lora_block()
+    desc: dict = {}
+    top, ca, plain_sd = make_lora_block(desc)
     g = torch.Generator().manual_seed(6)
     x, ctx = torch.randn(2, 64, 8, 8, generator=g), torch.randn(2, 5, 48, generator=g)
     top.set_context("cross_attention_block", {"ctx": ctx})
     with no_grad():
-        ref = top(x)
-    prev = B.set_fusion(fusion)
+        y = top(x)
+        ref = ounet.cross_attention_2d(ounet.Weights(plain_sd, loras=desc), "CrossAttentionBlock2d", x, ctx, 1, 1, True)
+    check(y, ref, "host")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+@pytest.mark.parametrize("fusion", ["merged", "two-launch", "unfused"])
+def test_lora_block_gpu(cuda_device, dtype, fusion):
+    """A LoRA-adapted CrossAttentionBlock2d (10 adapters, 2 LoRAs each) on the kernels against the oracle restatement
+    evaluated in fp32 on the CPU: with the merged-weight evaluation (default), the two-launch evaluation and unfused."""
+    from oracle import unet as ounet
+    from refiners_b200 import backend as B
+
+    desc: dict = {}
+    top, ca, plain_sd = make_lora_block(desc)
+    g = torch.Generator().manual_seed(6)
+    x, ctx = torch.randn(2, 64, 8, 8, generator=g), torch.randn(2, 5, 48, generator=g)
+    with no_grad():
+        ref = ounet.cross_attention_2d(ounet.Weights(plain_sd, loras=desc), "CrossAttentionBlock2d", x, ctx, 1, 1, True)
+    prev = B.set_fusion(fusion != "unfused")
+    prev_merge = B.set_lora_merge(fusion == "merged")
     try:
         top = top.to(cuda_device, dtype)
         top.set_context("cross_attention_block", {"ctx": ctx.to(cuda_device, dtype)})
@@ -225,4 +248,5 @@ def test_lora_block_gpu(cuda_device, dtype, fusion):
         check(y, ref, dtype)
     finally:
         B.set_fusion(prev)
+        B.set_lora_merge(prev_merge)
     assert launches > 0
