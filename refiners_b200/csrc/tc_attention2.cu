@@ -181,8 +181,20 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             ph_k ^= 1;
           }
           for (int j = 0; j < p.ntiles; ++j) {
-            const bool more = j + 1 < p.ntiles;
-            if (more) mbar_wait(&kv_full[st_k], ph_k, 6);  // K_{j+1} for the S tiles issued below
+            // S_g(j + 1) FIRST: a softmax group releases its S tile as soon as the values sit in its registers (early in
+            // tile j), so the next S can be computed while the group is still exponentiating - when it comes back for
+            // tile j + 1 the logits are already waiting in TMEM.  (Issuing S_g(j + 1) after P_g V(j), as the first version of
+            // this kernel did, put two MMA latencies on every group's critical path and let both groups fall into lock
+            // step: 4600 cycles per key tile instead of the ~2100 the exponentials need.)
+            if (j + 1 < p.ntiles) {
+              mbar_wait(&kv_full[st_k], ph_k, 6);  // K_{j+1}
+              issue_s(0, qb, st_k, s_issued[0]++);
+              issue_s(1, qb, st_k, s_issued[1]++);
+              if (++st_k == STAGES) {
+                st_k = 0;
+                ph_k ^= 1;
+              }
+            }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
               mbar_wait(&bar_p[g], t[g] & 1, 7);  // P_g(j) is in smem; O_g has been rescaled if it had to be
@@ -200,13 +212,8 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
               if (g == 1) umma_commit(&kv_empty[st_v]);  // both groups' P V (and, earlier, both S) have consumed this stage
               umma_commit(&bar_o[g]);
               ++t[g];
-              if (more) issue_s(g, qb, st_k, s_issued[g]++);
             }
             if (++st_v == STAGES) st_v = 0;
-            if (more && ++st_k == STAGES) {
-              st_k = 0;
-              ph_k ^= 1;
-            }
           }
           umma_commit(&q_empty[qb]);  // every MMA reading this Q buffer has been issued; it frees when they retire
         }
@@ -260,9 +267,15 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int i = 0; i < KT; ++i)
             if (i >= valid) s[i] = -INFINITY;
         }
-        float tmax = fmaxf(s[0], s[1]);
+        float tm0 = fmaxf(s[0], s[1]), tm1 = fmaxf(s[2], s[3]), tm2 = fmaxf(s[4], s[5]), tm3 = fmaxf(s[6], s[7]);
 #pragma unroll
-        for (int i = 2; i < KT; i += 2) tmax = fmaxf(tmax, fmaxf(s[i], s[i + 1]));
+        for (int i = 8; i < KT; i += 8) {  // four independent chains: the row maximum is on every tile's critical path
+          tm0 = fmaxf(tm0, fmaxf(s[i], s[i + 1]));
+          tm1 = fmaxf(tm1, fmaxf(s[i + 2], s[i + 3]));
+          tm2 = fmaxf(tm2, fmaxf(s[i + 4], s[i + 5]));
+          tm3 = fmaxf(tm3, fmaxf(s[i + 6], s[i + 7]));
+        }
+        const float tmax = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
         bool waited_o = false;
         if (j == 0) {
           m_run = tmax;  // nothing accumulated yet
@@ -424,7 +437,8 @@ int env_int(const char* name, int fallback) {
 }  // namespace
 
 // RB200_ATTN_V2: 0 = always the first-generation kernel, 1 (default) = this kernel where it applies.
-// RB200_ATTN_POLY: 1 = every fourth exponential on the FMA pipe (default), 0 = all on MUFU.
+// RB200_ATTN_POLY: 1 = every fourth exponential on the FMA pipe, 0 (default) = all on MUFU (measured: no gain with two
+// softmax warps per scheduler).
 bool tc_sdpa2_supported(const SdpaProblem& p) {
   static const int enabled = env_int("RB200_ATTN_V2", 1);
   if (!enabled) return false;
@@ -456,7 +470,7 @@ int tc_sdpa2(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_qk = common | (uint32_t(KT >> 3) << 17);                // D = 128 x 128, A and B K-major
   prm.idesc_pv = common | (uint32_t(HD >> 3) << 17) | (1u << 16);   // D = 128 x 64, B (= V) MN-major
   prm.d_out = p.D;
-  static const int poly = env_int("RB200_ATTN_POLY", 1);
+  static const int poly = env_int("RB200_ATTN_POLY", 0);
   const bool bf = p.dtype == RB200_BF16;
   if (poly) return bf ? launch<__nv_bfloat16, true>(st, mq, mk, mv, prm) : launch<__half, true>(st, mq, mk, mv, prm);
   return bf ? launch<__nv_bfloat16, false>(st, mq, mk, mv, prm) : launch<__half, false>(st, mq, mk, mv, prm);

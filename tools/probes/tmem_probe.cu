@@ -40,14 +40,16 @@ __global__ void tmem_ld_kernel(int iters, int mode, long long* cycles, uint32_t*
     if (mode == 0) {
       tmem_ld32(base, r0);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc ^= r0[i & 31];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc ^= r0[q];
     } else {
       tmem_ld32(base, r0);
       tmem_ld32(base + 32, r1);
       tmem_ld32(base + 64, r2);
       tmem_ld32(base + 96, r3);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      acc ^= r0[i & 31] ^ r1[i & 31] ^ r2[i & 31] ^ r3[i & 31];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) acc ^= r0[q] ^ r1[q] ^ r2[q] ^ r3[q];
     }
   }
   const long long t1 = clock64();
