@@ -80,3 +80,10 @@ __all__ = [
     "Module", "WeightedModule", "ContextModule", "Interpolate", "ReflectionPad2d", "PixelUnshuffle", "Converter",
     "MaxPool1d", "MaxPool2d", "ChainError", "ModuleTree",
 ]
+
+# reference-layout import paths (refiners.fluxion.layers.chain, .basics, .linear ...)
+import sys as _sys
+
+from refiners_b200.fluxion.layers import _paths, base as _base, composites as _composites, graph as _graph, leaves as _leaves, shape_ops as _shape_ops
+
+_paths.register(_sys.modules[__name__], (_graph, _base, _leaves, _shape_ops, _composites))

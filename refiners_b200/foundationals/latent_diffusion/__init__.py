@@ -3,8 +3,8 @@ from refiners_b200.foundationals.latent_diffusion.cross_attention import CrossAt
 from refiners_b200.foundationals.latent_diffusion.model import LatentDiffusionModel
 from refiners_b200.foundationals.latent_diffusion.range_adapter import RangeAdapter2d, RangeEncoder
 from refiners_b200.foundationals.latent_diffusion.solvers import DDIM, Euler, Solver, SolverParams
-from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1 import SD1UNet, StableDiffusion_1
-from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl import SDXLUNet, StableDiffusion_XL
+from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1 import SD1ControlnetAdapter, SD1UNet, StableDiffusion_1
+from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl import ControlLoraAdapter, SDXLUNet, StableDiffusion_XL
 from refiners_b200.foundationals.latent_diffusion.unet_blocks import (
     ResidualAccumulator,
     ResidualBlock,
@@ -15,4 +15,13 @@ __all__ = [
     "CrossAttentionBlock", "CrossAttentionBlock2d", "LatentDiffusionModel", "RangeAdapter2d", "RangeEncoder",
     "DDIM", "Euler", "Solver", "SolverParams", "SD1UNet", "StableDiffusion_1", "SDXLUNet", "StableDiffusion_XL",
     "ResidualAccumulator", "ResidualBlock", "ResidualConcatenator", "LatentDiffusionAutoencoder",
+    "SD1ControlnetAdapter", "ControlLoraAdapter", "SDXLIPAdapter",
 ]
+
+
+def __getattr__(name: str):
+    if name == "SDXLIPAdapter":
+        from refiners_b200.foundationals.latent_diffusion.image_prompt import SDXLIPAdapter
+
+        return SDXLIPAdapter
+    raise AttributeError(name)

@@ -28,6 +28,9 @@ def _alias_all() -> None:
         except Exception:  # optional sub-modules (PIL-dependent helpers ...) simply stay unaliased
             continue
         sys.modules["refiners" + info.name[len("refiners_b200"):]] = mod
+    for name, mod in list(sys.modules.items()):  # modules registered at import time (reference-layout views, see layers/_paths.py)
+        if name.startswith("refiners_b200."):
+            sys.modules.setdefault("refiners" + name[len("refiners_b200"):], mod)
 
 
 _alias_all()
