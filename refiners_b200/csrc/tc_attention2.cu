@@ -228,8 +228,13 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t lane_off = uint32_t(lg * 32) << 16;
     const uint32_t tmem_s = tmem_base + g * 128 + lane_off;
     const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_off;
-    uint8_t* prow = sP + g * P_BYTES + row * 128;
+    const uint32_t prow = smem_u32(sP + g * P_BYTES + row * 128);
     const int sw = row & 7;
+    // Turnstile between the two groups: only one of them exponentiates at a time.  Without it both groups receive their S
+    // tiles almost together and drift into lock step - both on the MUFU pipe (each at half rate), then both in their
+    // issue-bound phases (TMEM loads, row maximum, P stores) with the MUFU idle: 4850 cycles per key tile measured.  With
+    // it one group's exponentials hide the other group's everything-else.  Barrier id 1 + g opens group g's turn.
+    if (g == 1) named_bar_arrive(1, 256);  // group A goes first
     T* obase = static_cast<T*>(p.o);
     uint32_t t = 0;                       // tiles of this group so far
     uint32_t n = 0;
@@ -304,6 +309,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const float mb = m_run * p.scale_log2e;
         float psum0 = 0.f, psum1 = 0.f;
         uint32_t packed[KT / 2];
+        named_bar_sync(1 + g, 256);  // my turn on the MUFU pipe
 #pragma unroll
         for (int i = 0; i < KT; i += 4) {
           const float x0 = fmaf(s[i], p.scale_log2e, -mb), x1 = fmaf(s[i + 1], p.scale_log2e, -mb);
@@ -315,6 +321,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           packed[i / 2] = pack2<T>(p0, p1);
           packed[i / 2 + 1] = pack2<T>(p2, p3);
         }
+        named_bar_arrive(2 - g, 256);  // the other group's turn
         l_run += psum0 + psum1;
         // the P buffer of this group was last read by P V of tile t - 1
         if (j > 0 && !waited_o) mbar_wait(&bar_o[g], (t - 1) & 1, 11);
@@ -324,8 +331,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int q = sl * 32 + c * 4;
-            uint4 v = make_uint4(packed[q], packed[q + 1], packed[q + 2], packed[q + 3]);
-            *reinterpret_cast<uint4*>(prow + sl * P_SLAB + ((c ^ sw) << 4)) = v;
+            st_shared_v4(prow + sl * P_SLAB + ((c ^ sw) << 4), packed[q], packed[q + 1], packed[q + 2], packed[q + 3]);
           }
         }
         fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -372,6 +378,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   }
 
+  if (wg == 1) named_bar_sync(1, 256);  // consume group B's final hand-over: every named barrier ends balanced
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
