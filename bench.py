@@ -651,6 +651,7 @@ def run_gpu_arm(args) -> None:
             "parallelism": f"replicas x{world} (batch-sharded, no per-step collective)",
             "self_check": check, "adapters": extras.get("adapters"),
             "launches_per_replay": runner.launches_per_replay if runner else None,
+            "hoisted_step_invariant_ops": getattr(runner, "hoisted_ops", None) if runner else None,
         },
         "e2e": {"value": e2e_value, "unit": UNITS[cfg], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(gpu_launches),

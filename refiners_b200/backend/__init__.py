@@ -236,6 +236,59 @@ def clear_caches() -> None:
         cache.clear()
 
 
+# --------------------------------------------------------------- step-invariant hoisting (engine.graph)
+class InvariantMemo:
+    """Results of ops whose inputs do not change from one denoising step to the next.
+
+    A captured CUDA graph (refiners_b200.engine.graph) marks the static buffers of step-invariant contexts - the text
+    embedding, the IP-Adapter image embedding, a ControlNet / ControlLora condition image - with ``mark``.  While a memo
+    is active, ``linear`` / ``conv2d`` / ``unary`` on marked tensors run ONCE: the result is kept (and marked in turn,
+    so a chain of invariant ops such as ConditionEncoder's conv - SiLU stack is hoisted as a whole), later calls with
+    the same operands return it without launching anything - in particular the call made under stream capture, so the
+    graph replayed every step does not contain these kernels.  ``refresh`` recomputes every entry in place when the
+    owner sees an invariant context change (a new prompt).  SURVEY.md section 8f rank 2:
+    cross_attention.py:52-65 (text K / V projections), image_prompt.py:243-262, control_lora.py:193-201 of the reference."""
+
+    def __init__(self) -> None:
+        self.entries: dict[tuple[Any, ...], tuple[Tensor, Any]] = {}
+        self.hits = 0
+
+    @staticmethod
+    def mark(t: Tensor) -> Tensor:
+        t._rb200_invariant = True  # type: ignore[attr-defined]
+        return t
+
+    @staticmethod
+    def marked(*tensors: Tensor | None) -> bool:
+        return all(t is None or getattr(t, "_rb200_invariant", False) for t in tensors)
+
+    def fetch(self, key: tuple[Any, ...], thunk: Any) -> Tensor:
+        hit = self.entries.get(key)
+        if hit is not None:
+            self.hits += 1
+            return hit[0]
+        out = self.mark(thunk())
+        self.entries[key] = (out, thunk)
+        return out
+
+    def refresh(self) -> None:
+        for out, thunk in self.entries.values():  # insertion order = dependency order
+            out.copy_(thunk())
+
+    def __len__(self) -> int:
+        return len(self.entries)
+
+
+_memo: InvariantMemo | None = None
+
+
+def set_invariant_memo(memo: InvariantMemo | None) -> InvariantMemo | None:
+    """Activate (or, with None, deactivate) a memo; returns the previous one."""
+    global _memo
+    previous, _memo = _memo, memo
+    return previous
+
+
 # ------------------------------------------------------------------------- raw op kernels
 def _linear_impl(
     x: Tensor,
@@ -785,6 +838,9 @@ def linear(
             weight = merged_lora_weight(weight, loras)
         else:
             down, up, scale = pack_loras(x, weight, loras)
+    if _memo is not None and residual is None and InvariantMemo.marked(x):
+        return _memo.fetch(("linear", id(x), id(weight), id(bias), id(down), epilogue),
+                           lambda: _ops.linear(x, weight, bias, None, down, up, scale, epilogue))
     return _ops.linear(x, weight, bias, residual, down, up, scale, epilogue)
 
 
@@ -856,6 +912,20 @@ def conv2d(
     epilogue: int = EPI_NONE,
 ) -> Tensor:
     _inference_only(x, weight, bias)
+    if _memo is not None and chan_bias is None and residual is None and InvariantMemo.marked(x):
+        memo = _memo
+        key = ("conv2d", id(x), id(weight), id(bias), stride, padding, epilogue)
+        if key in memo.entries:
+            return memo.fetch(key, None)
+
+        def run() -> Tensor:
+            prev = set_invariant_memo(None)  # the body below must launch, not look itself up
+            try:
+                return conv2d(x, weight, bias, stride, padding, epilogue=epilogue)
+            finally:
+                set_invariant_memo(prev)
+
+        return memo.fetch(key, run)
     R, S = weight.shape[2], weight.shape[3]
     if (
         R == S == stride
@@ -965,6 +1035,8 @@ def layer_norm_2d(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
 
 def unary(x: Tensor, name: str) -> Tensor:
     _inference_only(x)
+    if _memo is not None and InvariantMemo.marked(x):
+        return _memo.fetch(("unary", id(x), name), lambda: _ops.unary(x, _UNARY[name]))
     return _ops.unary(x, _UNARY[name])
 
 

@@ -9,18 +9,22 @@
 //     that TMA brings in (half the L2 -> smem traffic per flop: two CTAs per SM each streaming their own K/V would need
 //     ~15 TB/s of L2 bandwidth at 1 PFLOP/s).
 //   * 128 keys per tile: S = Q K^T is a UMMA 128 x 128 x 16 (full-rate instruction shape), P V a 128 x 64 x 16 over 8 k-steps.
-//   * two softmax warpgroups, one per query tile, ping-pong against one MMA-issuing thread: while group A exponentiates
-//     tile j the tensor core computes S_B(j) / P_B V, and vice versa.
+//   * FOUR softmax warpgroups (two per query tile, each owning 64 of the tile's 128 key columns) against one MMA-issuing
+//     thread: four warps per scheduler keep the MUFU pipe fed (a single warp per scheduler reaches ~50 % of the pipe's
+//     rate - measured with ncu - because its own FADD / F2FP / FFMA stream and the MUFU latencies serialise with its
+//     MUFU issue), and while the groups of tile A exponentiate the tensor core computes S_B / P_B V, and vice versa.
 //   * the running output never leaves TMEM: the P V MMAs accumulate into one O tile per group, and the softmax keeps a
 //     STALE running maximum - O is rescaled in TMEM (tcgen05.ld / st) only when a row's maximum grows by more than 2^8
 //     (FlashAttention-4's conditional rescaling); the first kernel read 64 fp32 columns of O_j back per thread per tile.
-//   * S is read from TMEM exactly once per tile into registers (128 fp32 per thread; the softmax warpgroups raise their
-//     register budget with setmaxnreg, the TMA / MMA warpgroup gives its registers away).
+//   * S is read from TMEM exactly once per tile into registers (64 fp32 per thread); the two halves of a row exchange
+//     their partial maxima through shared memory (double buffered, one named barrier per tile) and keep partial row sums
+//     that are only combined when the row is written out.
 //   * optionally (POLY) every fourth exponential runs as a Cody-Waite cubic on the FMA pipe instead of MUFU.EX2: at head
 //     dim 64 the exponentials, not the MMAs, bound the kernel (16 MUFU lanes / clk / SM against 4096 MAC / clk / SM).
 //
-// Warps: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-3: idle}; warpgroup 1 = softmax of
-// query tile A; warpgroup 2 = softmax of query tile B.  thread = query row = TMEM lane.
+// Warps: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-3: idle}; warpgroups 1, 2 = softmax
+// of query tile A (key columns 0-63 / 64-127); warpgroups 3, 4 = softmax of query tile B.  thread = (query row = TMEM
+// lane, column half).
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
 // smem: Q 2 x (2 x 16 KB) (double buffered across work items), K/V ring 3 x (16 + 16 KB), P_A, P_B 32 KB each.
 #include <cuda.h>
@@ -39,14 +43,15 @@ constexpr int QT = 128;             // queries per tile (UMMA M)
 constexpr int KT = 128;             // keys per tile (UMMA N of S, K extent of P V)
 constexpr int HD = 64;              // head-dim slab (columns >= D are zero filled by TMA)
 constexpr int STAGES = 3;
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 640;
 constexpr int Q_TILE_BYTES = QT * HD * 2;      // 16 KB
 constexpr int Q_BYTES = 2 * Q_TILE_BYTES;      // both tiles of a pair
 constexpr int K_BYTES = KT * HD * 2, V_BYTES = KT * HD * 2;
 constexpr int P_SLAB = QT * 64 * 2;            // 64 keys of P for 128 rows: one 128-byte-row swizzle slab
 constexpr int P_BYTES = 2 * P_SLAB;            // 128 keys
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int XCHG_BYTES = 2 /*groups*/ * 2 /*tile parity*/ * 2 /*halves*/ * QT * 4;   // partial row maxima (also reused for the row sums)
+constexpr size_t SMEM_BYTES = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XCHG_BYTES;
 constexpr float RESCALE_LOG2 = 8.0f;           // tolerate a stale maximum until a probability could exceed 2^8
 
 struct Attn2Params {
@@ -93,6 +98,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_o = q_full + 10;                // [2] every P V issued so far for the group has landed in O
   uint64_t* bar_ofree = q_full + 12;            // [2] the finished work item's O rows have been read out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
+  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [group][parity][half][row]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = warp >> 2;
@@ -109,10 +115,10 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
       mbar_init(&bar_s[b], 1);
-      mbar_init(&bar_sfree[b], 4);
-      mbar_init(&bar_p[b], 4);
+      mbar_init(&bar_sfree[b], 8);   // 2 column halves x 4 warps
+      mbar_init(&bar_p[b], 8);
       mbar_init(&bar_o[b], 1);
-      mbar_init(&bar_ofree[b], 4);
+      mbar_init(&bar_ofree[b], 8);
     }
     fence_barrier_init();
   }
@@ -123,7 +129,7 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (wg == 0) {
-    setmaxnreg_dec<72>();
+    setmaxnreg_dec<56>();
     if (warp == 0) {
       // ================================================================================ TMA
       if (lane == 0) {
@@ -221,20 +227,18 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     }
   } else {
     // ============================================================================ softmax
-    setmaxnreg_inc<216>();
-    const int g = wg - 1;                 // query tile of the pair
+    setmaxnreg_inc<104>();
+    const int g = (wg - 1) >> 1;          // query tile of the pair
+    const int hf = (wg - 1) & 1;          // which 64 key columns of the tile (and which 32 output columns) this thread owns
     const int lg = warp & 3;              // TMEM lane group of this warp
     const int row = lg * 32 + lane;
     const uint32_t lane_off = uint32_t(lg * 32) << 16;
-    const uint32_t tmem_s = tmem_base + g * 128 + lane_off;
-    const uint32_t tmem_o = tmem_base + 256 + g * 64 + lane_off;
-    const uint32_t prow = smem_u32(sP + g * P_BYTES + row * 128);
+    const uint32_t tmem_s = tmem_base + g * 128 + hf * 64 + lane_off;
+    const uint32_t tmem_o = tmem_base + 256 + g * 64 + hf * 32 + lane_off;
+    const uint32_t prow = smem_u32(sP + g * P_BYTES + hf * P_SLAB + row * 128);
     const int sw = row & 7;
-    // Turnstile between the two groups: only one of them exponentiates at a time.  Without it both groups receive their S
-    // tiles almost together and drift into lock step - both on the MUFU pipe (each at half rate), then both in their
-    // issue-bound phases (TMEM loads, row maximum, P stores) with the MUFU idle: 4850 cycles per key tile measured.  With
-    // it one group's exponentials hide the other group's everything-else.  Barrier id 1 + g opens group g's turn.
-    if (g == 1) named_bar_arrive(1, 256);  // group A goes first
+    float* xg = xchg + g * (2 * 2 * QT);  // this group's exchange area: [parity][half][row]
+    const uint32_t xbar = 1 + g;          // named barrier of the group's 256 threads
     T* obase = static_cast<T*>(p.o);
     uint32_t t = 0;                       // tiles of this group so far
     uint32_t n = 0;
@@ -242,65 +246,66 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int pair = int(w % p.n_pairs);
       const int h = int((w / p.n_pairs) % p.H);
       const int64_t b = w / (int64_t(p.n_pairs) * p.H);
-      float m_run = -INFINITY, l_run = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;  // l_run: this half's share of the row sum
       for (int j = 0; j < p.ntiles; ++j, ++t) {
         mbar_wait(&bar_s[g], t & 1, 9);
         tcgen05_fence_after();
-        float s[KT];
+        float s[KT / 2];
         {
-          uint32_t r0[32], r1[32], r2[32], r3[32];
+          uint32_t r0[32], r1[32];
           tmem_ld_32x32(tmem_s, r0);
           tmem_ld_32x32(tmem_s + 32, r1);
-          tmem_ld_32x32(tmem_s + 64, r2);
-          tmem_ld_32x32(tmem_s + 96, r3);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             s[i] = __uint_as_float(r0[i]);
             s[32 + i] = __uint_as_float(r1[i]);
-            s[64 + i] = __uint_as_float(r2[i]);
-            s[96 + i] = __uint_as_float(r3[i]);
           }
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(&bar_sfree[g]);  // the tensor core may overwrite this S tile
-        const int64_t left = p.Sk - int64_t(j) * KT;
-        if (left < KT) {
-          const int valid = int(left);
+        const int64_t left = p.Sk - int64_t(j) * KT - hf * 64;  // valid keys among this thread's 64 columns
+        if (left < 64) {
+          const int valid = left > 0 ? int(left) : 0;
 #pragma unroll
-          for (int i = 0; i < KT; ++i)
+          for (int i = 0; i < 64; ++i)
             if (i >= valid) s[i] = -INFINITY;
         }
         float tm0 = fmaxf(s[0], s[1]), tm1 = fmaxf(s[2], s[3]), tm2 = fmaxf(s[4], s[5]), tm3 = fmaxf(s[6], s[7]);
 #pragma unroll
-        for (int i = 8; i < KT; i += 8) {  // four independent chains: the row maximum is on every tile's critical path
+        for (int i = 8; i < 64; i += 8) {  // four independent chains: the row maximum is on every tile's critical path
           tm0 = fmaxf(tm0, fmaxf(s[i], s[i + 1]));
           tm1 = fmaxf(tm1, fmaxf(s[i + 2], s[i + 3]));
           tm2 = fmaxf(tm2, fmaxf(s[i + 4], s[i + 5]));
           tm3 = fmaxf(tm3, fmaxf(s[i + 6], s[i + 7]));
         }
-        const float tmax = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
+        // the row maximum of the tile = max over both column halves: exchange through smem (slot parity t & 1: a thread is
+        // never more than one tile ahead of its partner, which may still be reading the previous tile's slot)
+        float* slot = xg + (t & 1) * (2 * QT);
+        const float mine = fmaxf(fmaxf(tm0, tm1), fmaxf(tm2, tm3));
+        slot[hf * QT + row] = mine;
+        named_bar_sync(xbar, 256);
+        const float tmax = fmaxf(mine, slot[(hf ^ 1) * QT + row]);
         bool waited_o = false;
         if (j == 0) {
           m_run = tmax;  // nothing accumulated yet
         } else {
           const float m_new = fmaxf(m_run, tmax);
           const bool grew = (m_new - m_run) * p.scale_log2e > RESCALE_LOG2;
-          if (__any_sync(0xffffffffu, grew)) {  // TMEM access is warp-collective: the whole warp rescales its 32 rows
+          // TMEM access is warp-collective: the whole warp rescales its 32 rows; the partner warp (same rows, other column
+          // half) sees the same maxima and takes the same decision for its 32 output columns
+          if (__any_sync(0xffffffffu, grew)) {
             mbar_wait(&bar_o[g], (t - 1) & 1, 10);  // every P V issued so far has landed in O
             waited_o = true;
             tcgen05_fence_after();
             const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_o, raw);
+            tmem_ld_wait();
 #pragma unroll
-            for (int half = 0; half < HD / 32; ++half) {
-              uint32_t raw[32];
-              tmem_ld_32x32(tmem_o + half * 32, raw);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-              tmem_st_32x32(tmem_o + half * 32, raw);
-            }
+            for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+            tmem_st_32x32(tmem_o, raw);
             tmem_st_wait();
             l_run *= alpha;
             m_run = m_new;
@@ -308,60 +313,61 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         const float mb = m_run * p.scale_log2e;
         float psum0 = 0.f, psum1 = 0.f;
-        uint32_t packed[KT / 2];
-        named_bar_sync(1 + g, 256);  // my turn on the MUFU pipe
-#pragma unroll
-        for (int i = 0; i < KT; i += 4) {
-          const float x0 = fmaf(s[i], p.scale_log2e, -mb), x1 = fmaf(s[i + 1], p.scale_log2e, -mb);
-          const float x2 = fmaf(s[i + 2], p.scale_log2e, -mb), x3 = fmaf(s[i + 3], p.scale_log2e, -mb);
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2);
-          const float p3 = POLY ? ex2_poly(x3) : ex2_approx(x3);
-          psum0 += p0 + p1;
-          psum1 += p2 + p3;
-          packed[i / 2] = pack2<T>(p0, p1);
-          packed[i / 2 + 1] = pack2<T>(p2, p3);
-        }
-        named_bar_arrive(2 - g, 256);  // the other group's turn
-        l_run += psum0 + psum1;
-        // the P buffer of this group was last read by P V of tile t - 1
+        // the P buffer of this group was last read by P V of tile t - 1 (issued a whole tile ago): wait for it BEFORE the
+        // exponentials, so that every 16-byte chunk of P goes to shared memory as soon as it exists (4 live registers
+        // instead of 32)
         if (j > 0 && !waited_o) mbar_wait(&bar_o[g], (t - 1) & 1, 11);
         if (j == 0 && t > 0) mbar_wait(&bar_o[g], (t - 1) & 1, 12);  // ... of the previous work item's last tile
 #pragma unroll
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int c = 0; c < 8; ++c) {
+          uint32_t pk[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int q = sl * 32 + c * 4;
-            st_shared_v4(prow + sl * P_SLAB + ((c ^ sw) << 4), packed[q], packed[q + 1], packed[q + 2], packed[q + 3]);
+          for (int q = 0; q < 2; ++q) {
+            const int i = c * 8 + q * 4;
+            const float x0 = fmaf(s[i], p.scale_log2e, -mb), x1 = fmaf(s[i + 1], p.scale_log2e, -mb);
+            const float x2 = fmaf(s[i + 2], p.scale_log2e, -mb), x3 = fmaf(s[i + 3], p.scale_log2e, -mb);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2);
+            const float p3 = POLY ? ex2_poly(x3) : ex2_approx(x3);
+            psum0 += p0 + p1;
+            psum1 += p2 + p3;
+            pk[q * 2] = pack2<T>(p0, p1);
+            pk[q * 2 + 1] = pack2<T>(p2, p3);
           }
+          st_shared_v4(prow + ((c ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
+        l_run += psum0 + psum1;
         fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
         tcgen05_fence_before();   // also orders a rescale's tcgen05.st before the MMA that the arrive releases
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[g]);
       }
-      // ---- read the finished rows out of TMEM
+      // ---- row sum = both halves' shares; read the finished rows out of TMEM (32 output columns per thread)
+      float* slot = xg + (t & 1) * (2 * QT);   // parity of the NEXT tile: free (its last use was two tiles ago)
+      slot[hf * QT + row] = l_run;
+      named_bar_sync(xbar, 256);
+      const float l_row = l_run + slot[(hf ^ 1) * QT + row];
+      named_bar_sync(xbar, 256);               // both halves have read before the next work item's first tile rewrites the slot
       mbar_wait(&bar_o[g], (t - 1) & 1, 13);
       tcgen05_fence_after();
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      float acc[HD];
-#pragma unroll
-      for (int half = 0; half < HD / 32; ++half) {
+      const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+      float acc[32];
+      {
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_o + half * 32, raw);
+        tmem_ld_32x32(tmem_o, raw);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[half * 32 + i] = inv * __uint_as_float(raw[i]);
+        for (int i = 0; i < 32; ++i) acc[i] = inv * __uint_as_float(raw[i]);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(&bar_ofree[g]);  // the MMA warp may start the next work item's P V
       const int64_t qi = (int64_t(pair) * 2 + g) * QT + row;
       if (qi < p.Sq) {
-        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out;
+        T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out + hf * 32;
         if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (p.d_out & 7) == 0) {
 #pragma unroll
-          for (int c = 0; c < HD / 8; ++c) {
-            if (c * 8 >= p.d_out) break;
+          for (int c = 0; c < 4; ++c) {
+            if (hf * 32 + c * 8 >= p.d_out) break;
             uint4 v;
             v.x = pack2<T>(acc[c * 8], acc[c * 8 + 1]);
             v.y = pack2<T>(acc[c * 8 + 2], acc[c * 8 + 3]);
@@ -371,14 +377,13 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < HD; ++i)
-            if (i < p.d_out) dst[i] = from_f<T>(acc[i]);
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i < p.d_out) dst[i] = from_f<T>(acc[i]);
         }
       }
     }
   }
 
-  if (wg == 1) named_bar_sync(1, 256);  // consume group B's final hand-over: every named barrier ends balanced
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -25,6 +25,13 @@ What a capture bakes in, and how each is kept honest:
                                        use the same stamp); writes through ``.data`` are invisible to
                                        autograd's version counter - call ``invalidate()`` after those.
 
+Step-invariant hoisting.  Some context tensors do not change from one denoising step to
+the next: the text embedding, the IP-Adapter image embedding, a ControlNet / ControlLora condition image.  Everything
+computed from them alone - the K / V projections of every cross-attention (cross_attention.py:52-65 of the reference),
+the IP-Adapter's K' / V' (image_prompt.py:243-262), the ConditionEncoder (control_lora.py:193-201) - is computed ONCE,
+outside the captured graph (backend.InvariantMemo), and recomputed only when the caller passes a different tensor (or
+the same tensor with a bumped version) for such a context.  ``RB200_HOIST=0`` keeps everything inside the graph.
+
 ``set_context`` is observed, not swallowed: the providers keep receiving the values, so an eager call of
 the same chain (debugging, a CPU fallback of the caller) still sees its contexts.  Python side effects
 of a forward (residual lists, size stacks) happen at capture time only and are undone by
@@ -33,8 +40,9 @@ of a forward (residual lists, size stacks) happen at capture time only and are u
 
 from __future__ import annotations
 
+import os
 import weakref
-from typing import Any
+from typing import Any, Callable
 
 import torch
 from torch import Tensor
@@ -45,6 +53,15 @@ from refiners_b200.fluxion.layers.base import value_epoch
 from refiners_b200.fluxion.layers.graph import Chain, structure_epoch
 
 
+def step_invariant(context: str, key: str) -> bool:
+    """Default classification of context entries that stay the same over a denoising loop."""
+    return key in ("clip_text_embedding", "clip_image_embedding") or key.startswith("condition")
+
+
+def _stamp_of(t: Tensor) -> tuple[int, int, tuple[int, ...]]:
+    return (t.data_ptr(), t._version, tuple(t.shape))
+
+
 def _signature(v: Any) -> Any:
     if isinstance(v, Tensor):
         return ("tensor", tuple(v.shape), v.dtype)
@@ -52,9 +69,14 @@ def _signature(v: Any) -> Any:
 
 
 class GraphedChain:
-    def __init__(self, chain: Chain, warmup: int = 2) -> None:
+    def __init__(self, chain: Chain, warmup: int = 2, invariant: Callable[[str, str], bool] | None = step_invariant) -> None:
         self.chain = chain
         self.warmup = warmup
+        self.invariant = invariant if os.environ.get("RB200_HOIST", "1") != "0" else None
+        self._memo: B.InvariantMemo | None = None
+        self._seen: dict[tuple[int, str, str], Any] = {}   # identity stamps of the invariant context tensors last copied
+        self.hoisted_ops = 0
+        self.refreshes = 0
         self._graph: torch.cuda.CUDAGraph | None = None
         self._epochs: tuple[int, int] = (-1, -1)
         self._pending: dict[tuple[int, str], dict[str, Any]] = {}   # (id(owner), context) -> values
@@ -145,19 +167,31 @@ class GraphedChain:
             for key, v in values.items()
             if isinstance(v, Tensor)
         }
-        side = torch.cuda.Stream(device=device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):  # warm-up off the capture: packs weights, sizes the allocator
-            for _ in range(self.warmup):
-                self._apply_contexts()
-                self.chain(*self._static_in)
-        torch.cuda.current_stream(device).wait_stream(side)
-        self._apply_contexts()
-        graph = torch.cuda.CUDAGraph()
-        before = B.launch_count()
-        with torch.cuda.graph(graph):
-            self._static_out = self.chain(*self._static_in)
-        self.launches_per_replay = B.launch_count() - before
+        self._memo, self._seen = None, {}
+        if self.invariant is not None:
+            self._memo = B.InvariantMemo()
+            for (oid, context, key), buf in self._static.items():
+                if self.invariant(context, key):
+                    B.InvariantMemo.mark(buf)
+                    self._seen[(oid, context, key)] = _stamp_of(self._pending[(oid, context)][key])
+        previous_memo = B.set_invariant_memo(self._memo)
+        try:
+            side = torch.cuda.Stream(device=device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):  # warm-up off the capture: packs weights, sizes the allocator, fills the memo
+                for _ in range(self.warmup):
+                    self._apply_contexts()
+                    self.chain(*self._static_in)
+            torch.cuda.current_stream(device).wait_stream(side)
+            self._apply_contexts()
+            graph = torch.cuda.CUDAGraph()
+            before = B.launch_count()
+            with torch.cuda.graph(graph):
+                self._static_out = self.chain(*self._static_in)
+            self.launches_per_replay = B.launch_count() - before
+        finally:
+            B.set_invariant_memo(previous_memo)
+        self.hoisted_ops = len(self._memo) if self._memo is not None else 0
         self._restore_contexts()
         self._graph = graph
         self._epochs = (structure_epoch(), value_epoch())
@@ -179,10 +213,22 @@ class GraphedChain:
         else:
             for buf, new in zip(self._static_in, inputs):
                 buf.copy_(new, non_blocking=True)
+            changed = False
             for (oid, context), values in self._pending.items():
                 for key, v in values.items():
-                    if isinstance(v, Tensor):
-                        self._static[(oid, context, key)].copy_(v, non_blocking=True)
+                    if not isinstance(v, Tensor):
+                        continue
+                    slot = (oid, context, key)
+                    if slot in self._seen:  # step-invariant: copied (and its dependants recomputed) only when it changed
+                        stamp = _stamp_of(v)
+                        if stamp == self._seen[slot]:
+                            continue
+                        self._seen[slot] = stamp
+                        changed = True
+                    self._static[slot].copy_(v, non_blocking=True)
+            if changed and self._memo is not None:
+                self._memo.refresh()
+                self.refreshes += 1
         assert self._graph is not None
         self._graph.replay()
         self.replays += 1

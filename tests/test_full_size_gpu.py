@@ -127,6 +127,20 @@ def test_config2_sdxl_unet_full_size(cuda_device, api, base_weights, golden, fas
         y_cpu_ctx = runner(x).clone()
         cases.set_sdxl_contexts(unet, dict(inp, timestep=torch.tensor([250.0])), cuda_device, BF16)
         assert torch.equal(y_cpu_ctx, unet(x)), "CPU timestep / time_ids were baked into the capture"
+        # step-invariant hoisting: the text K / V projections live outside the graph; a NEW prompt (another tensor, or the
+        # same tensor modified in place) must be picked up by the next call
+        if runner.invariant is not None:
+            assert runner.hoisted_ops >= 70, f"only {runner.hoisted_ops} step-invariant ops hoisted out of the graph"
+        other = cases.keyed_input("cfg2.other_ctx", (2, 77, 2048)).to(cuda_device, BF16)
+        for new_ctx in (other, other.mul_(0.5)):  # second round: same object, bumped version
+            inp_new = dict(inp, ctx=new_ctx)
+            cases.set_sdxl_contexts(unet, inp_new, cuda_device, BF16)
+            y_new_graph = runner(x).clone()
+            cases.set_sdxl_contexts(unet, inp_new, cuda_device, BF16)
+            y_new_eager = unet(x)
+            assert torch.equal(y_new_graph, y_new_eager), "stale text K / V projections after a prompt change"
+            assert not torch.equal(y_new_graph, y_cpu_ctx)
+        assert runner.captures == 1, "a prompt change must refresh the hoisted results, not re-capture"
         runner.close()
 
 
