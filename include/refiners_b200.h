@@ -145,6 +145,18 @@ int rb200_geglu(void* stream, int dtype, const void* x, void* y, int64_t rows, i
 /* y = a + alpha * b (Residual / Sum of fluxion/layers/chain.py:867-927; Multiply of basics.py:379) */
 int rb200_add(void* stream, int dtype, const void* a, const void* b, void* y, int64_t n, float alpha);
 
+/* ---- Denoising-step glue --------------------------------------------------------------------
+ * The elementwise part of one LatentDiffusionModel.forward (foundationals/latent_diffusion/model.py:137-159) with the
+ * Euler solver (solvers/euler.py:63-100), two launches instead of one per arithmetic operator; every intermediate is
+ * rounded to `dtype` exactly where the reference's operator-by-operator evaluation rounds it (bit-identical results).
+ *   rb200_cfg_scale_input: y[i] (= y[n + i] when twice != 0: torch.cat((x, x)) of classifier-free guidance)
+ *                            = x[i] / ((sigma^2 + 1) ^ 0.5),           sigma = *sigma (device scalar of `dtype`)
+ *   rb200_cfg_euler:       noise = guided ? u + condition_scale * (c - u) : eps,  (u, c) = eps[i], eps[n + i]
+ *                          y[i] = x[i] + noise * (sigmas[1] - sigmas[0])          (sigmas: two consecutive device scalars) */
+int rb200_cfg_scale_input(void* stream, int dtype, const void* x, void* y, int64_t n, const void* sigma, int twice);
+int rb200_cfg_euler(void* stream, int dtype, const void* x, const void* eps, void* y, int64_t n, const void* sigmas,
+                    float condition_scale, int guided);
+
 /* ---- SAM ViT data movement ------------------------------------------------------------------
  * Patch embedding (foundationals/segment_anything/image_encoder.py:9-34 PatchEncoder: Conv2d with
  * kernel = stride = P) is a GEMM over non-overlapping patches; rb200_patchify lays them out as rows:

@@ -90,6 +90,8 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_unary": (_I, [_P, _I, _P, _P, _L, _I]),
     "rb200_geglu": (_I, [_P, _I, _P, _P, _L, _L]),
     "rb200_add": (_I, [_P, _I, _P, _P, _P, _L, _F]),
+    "rb200_cfg_scale_input": (_I, [_P, _I, _P, _P, _L, _P, _I]),
+    "rb200_cfg_euler": (_I, [_P, _I, _P, _P, _P, _L, _P, _F, _I]),
     "rb200_sdpa": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _L, _L, _I] + [_L] * 8 + [_F, _I, _P, _P, _L] + [_L] * 4 + [_F]),
     "rb200_sam_attention_workspace_bytes": (_Z, [_L, _I, _I, _I, _I]),
     "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
@@ -1048,6 +1050,35 @@ def geglu(x: Tensor) -> Tensor:
 def add(a: Tensor, b: Tensor, alpha: float = 1.0) -> Tensor:
     _inference_only(a, b)
     return _ops.add(a, b, alpha)
+
+
+def cfg_scale_input(x: Tensor, sigmas: Tensor, step: int, twice: bool) -> Tensor:
+    """``cat((x, x)) / ((sigmas[step]^2 + 1)^0.5)`` (or without the doubling) in one launch; see rb200_cfg_scale_input."""
+    _inference_only(x)
+    _same(x, sigmas)
+    lib = load_library()
+    xc = x.contiguous()
+    y = torch.empty(((2 if twice else 1) * xc.shape[0], *xc.shape[1:]), device=x.device, dtype=x.dtype)
+    sigma = sigmas[step : step + 1]
+    with torch.cuda.device(x.device):
+        _check(lib.rb200_cfg_scale_input(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), xc.numel(), sigma.data_ptr(), int(twice)))
+    return y
+
+
+def cfg_euler(x: Tensor, eps: Tensor, sigmas: Tensor, step: int, condition_scale: float, guided: bool) -> Tensor:
+    """``x + (u + s (c - u)) * (sigmas[step + 1] - sigmas[step])`` in one launch; see rb200_cfg_euler."""
+    _inference_only(x, eps)
+    _same(x, eps, sigmas)
+    lib = load_library()
+    xc, ec = x.contiguous(), eps.contiguous()
+    if ec.numel() != (2 if guided else 1) * xc.numel():
+        raise BackendError(f"cfg_euler: noise prediction {tuple(eps.shape)} does not match latents {tuple(x.shape)} (guided={guided})")
+    y = torch.empty_like(xc)
+    pair = sigmas[step : step + 2]
+    with torch.cuda.device(x.device):
+        _check(lib.rb200_cfg_euler(_stream(), _dtype_code(x), xc.data_ptr(), ec.data_ptr(), y.data_ptr(), xc.numel(), pair.data_ptr(),
+                                   float(condition_scale), int(guided)))
+    return y
 
 
 def sdpa(

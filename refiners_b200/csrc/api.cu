@@ -47,6 +47,8 @@ int layer_norm_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, flo
 int unary_impl(cudaStream_t, int, const void*, void*, int64_t, int);
 int add_impl(cudaStream_t, int, const void*, const void*, void*, int64_t, float);
 int geglu_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t);
+int cfg_scale_input_impl(cudaStream_t, int, const void*, void*, int64_t, const void*, int);
+int cfg_euler_impl(cudaStream_t, int, const void*, const void*, void*, int64_t, const void*, float, int);
 int patchify_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t);
 int window_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
 int pad_channels_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, int64_t);
@@ -203,6 +205,19 @@ int rb200_geglu(void* stream, int dtype, const void* x, void* y, int64_t rows, i
   if (bad_dtype(dtype) || !x || !y) RB200_FAIL(-1, "geglu: bad arguments");
   if (rows <= 0 || F <= 0) return 0;
   return geglu_impl(static_cast<cudaStream_t>(stream), dtype, x, y, rows, F);
+}
+
+int rb200_cfg_scale_input(void* stream, int dtype, const void* x, void* y, int64_t n, const void* sigma, int twice) {
+  if (bad_dtype(dtype) || !x || !y || !sigma) RB200_FAIL(-1, "cfg_scale_input: bad arguments");
+  if (n <= 0) return 0;
+  return cfg_scale_input_impl(static_cast<cudaStream_t>(stream), dtype, x, y, n, sigma, twice);
+}
+
+int rb200_cfg_euler(void* stream, int dtype, const void* x, const void* eps, void* y, int64_t n, const void* sigmas, float condition_scale,
+                    int guided) {
+  if (bad_dtype(dtype) || !x || !eps || !y || !sigmas) RB200_FAIL(-1, "cfg_euler: bad arguments");
+  if (n <= 0) return 0;
+  return cfg_euler_impl(static_cast<cudaStream_t>(stream), dtype, x, eps, y, n, sigmas, condition_scale, guided);
 }
 
 int rb200_add(void* stream, int dtype, const void* a, const void* b, void* y, int64_t n, float alpha) {

@@ -675,6 +675,54 @@ int add_impl(cudaStream_t st, int dtype, const void* a, const void* b, void* y, 
   return 0;
 }
 
+// ---------------------------------------------------------------- denoising-step glue (CFG + Euler)
+// The reference evaluates these with one ATen kernel per arithmetic operator, each rounding its result to the tensor
+// dtype (model.py:137-159, solvers/euler.py:63-100).  The fused kernels reproduce that rounding sequence (`rn<T>`), so
+// a step through them is bit-identical to the operator-by-operator evaluation.
+template <typename T> __device__ __forceinline__ float rn(float v) { return to_f(from_f<T>(v)); }
+
+// y[i] (and y[n + i] when `twice`: the unconditional / conditional halves of classifier-free guidance are the same latents)
+//   = x[i] / ((sigma^2 + 1) ^ 0.5),  sigma = sigmas[0]
+template <typename T>
+__global__ void cfg_scale_input_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, const T* __restrict__ sigmas, int twice) {
+  const float sigma = to_f(sigmas[0]);
+  // __f*_rn: no FMA contraction - the operator sequence rounds after every multiply and every add, also in fp32
+  const float denom = rn<T>(__fsqrt_rn(rn<T>(__fadd_rn(rn<T>(__fmul_rn(sigma, sigma)), 1.0f))));
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const T v = from_f<T>(__fdiv_rn(to_f(x[i]), denom));
+    y[i] = v;
+    if (twice) y[n + i] = v;
+  }
+}
+
+// eps: [2n] = (unconditional | conditional) when `guided`, else [n].
+//   noise = u + scale * (c - u);   y = x + noise * (sigmas[1] - sigmas[0])
+template <typename T>
+__global__ void cfg_euler_kernel(const T* __restrict__ x, const T* __restrict__ eps, T* __restrict__ y, int64_t n,
+                                 const T* __restrict__ sigmas, float scale, int guided) {
+  const float dsigma = rn<T>(__fsub_rn(to_f(sigmas[1]), to_f(sigmas[0])));
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    float noise = to_f(eps[i]);
+    if (guided) {
+      const float u = noise, c = to_f(eps[n + i]);
+      noise = rn<T>(__fadd_rn(u, rn<T>(__fmul_rn(scale, rn<T>(__fsub_rn(c, u))))));
+    }
+    y[i] = from_f<T>(__fadd_rn(to_f(x[i]), rn<T>(__fmul_rn(noise, dsigma))));
+  }
+}
+
+int cfg_scale_input_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t n, const void* sigmas, int twice) {
+  DISPATCH_T(dtype, { cfg_scale_input_kernel<T><<<ew_grid(n), 256, 0, st>>>((const T*)x, (T*)y, n, (const T*)sigmas, twice); });
+  RB200_CHECK_LAUNCH("cfg_scale_input");
+  return 0;
+}
+
+int cfg_euler_impl(cudaStream_t st, int dtype, const void* x, const void* eps, void* y, int64_t n, const void* sigmas, float scale, int guided) {
+  DISPATCH_T(dtype, { cfg_euler_kernel<T><<<ew_grid(n), 256, 0, st>>>((const T*)x, (const T*)eps, (T*)y, n, (const T*)sigmas, scale, guided); });
+  RB200_CHECK_LAUNCH("cfg_euler");
+  return 0;
+}
+
 int geglu_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t rows, int64_t F) {
   DISPATCH_T(dtype, {
     constexpr int V = 16 / sizeof(T);

@@ -26,7 +26,7 @@
 // of query tile A (key columns 0-63 / 64-127); warpgroups 3, 4 = softmax of query tile B.  thread = (query row = TMEM
 // lane, column half).
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
-// smem: Q 2 x (2 x 16 KB) (double buffered across work items), K/V ring 3 x (16 + 16 KB), P_A, P_B 32 KB each.
+// smem: Q 2 x (2 x 16 KB) (double buffered across work items), K/V ring 2 x (16 + 16 KB), P_A, P_B 32 KB each, 4 KB exchange.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -42,7 +42,7 @@ using namespace ptx;
 constexpr int QT = 128;             // queries per tile (UMMA M)
 constexpr int KT = 128;             // keys per tile (UMMA N of S, K extent of P V)
 constexpr int HD = 64;              // head-dim slab (columns >= D are zero filled by TMA)
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;  // K/V ring: a tile (32 KB) is in use for ~2 us, TMA needs ~1 us to refill its slot
 constexpr int NUM_THREADS = 640;
 constexpr int Q_TILE_BYTES = QT * HD * 2;      // 16 KB
 constexpr int Q_BYTES = 2 * Q_TILE_BYTES;      // both tiles of a pair
@@ -52,6 +52,7 @@ constexpr int P_BYTES = 2 * P_SLAB;            // 128 keys
 constexpr int TMEM_COLS = 512;
 constexpr int XCHG_BYTES = 2 /*groups*/ * 2 /*tile parity*/ * 2 /*halves*/ * QT * 4;   // partial row maxima (also reused for the row sums)
 constexpr size_t SMEM_BYTES = 2 * Q_BYTES + STAGES * (K_BYTES + V_BYTES) + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XCHG_BYTES;
+static_assert(SMEM_BYTES <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
 constexpr float RESCALE_LOG2 = 8.0f;           // tolerate a stale maximum until a probability could exceed 2^8
 
 struct Attn2Params {

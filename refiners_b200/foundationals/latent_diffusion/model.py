@@ -1,9 +1,20 @@
-"""One denoising step: classifier-free-guidance batching, UNet call, solver update.
+"""One denoising step of a latent diffusion model: guidance batching, UNet call, guidance combine, solver update.
 
-Follows /root/reference/src/refiners/foundationals/latent_diffusion/model.py:15-169
-(`LatentDiffusionModel.forward` :128-159).  Scope note: the VAE (`lda`) and the CLIP text
-encoder run once per image/prompt, outside the per-step hot path, and are not rebuilt here
-(SURVEY.md section 8f); they are optional constructor arguments and any fluxion Chain works.
+Contract (constructor, ``forward`` signature and semantics, ``init_latents`` / ``sample_noise`` / ``steps`` /
+``set_inference_steps`` / ``structural_copy``) from
+/root/reference/src/refiners/foundationals/latent_diffusion/model.py:15-169 (``forward`` :128-159).
+
+The step is written here as three stages - *prepare* the model input, *predict* the noise, *advance* the latents - so
+that the CUDA path can swap each stage for its fused form without changing what is computed:
+
+  prepare   ``scale_model_input(cat((x, x)))``                    one launch (rb200_cfg_scale_input) for the Euler solver
+  predict   the UNet, replayed from a captured CUDA graph when ``enable_cuda_graph()`` is on; text / image-prompt K, V
+            projections and condition encoders are hoisted out of the per-step graph (engine.graph)
+  advance   ``uncond + s * (cond - uncond)`` then the solver update    one launch (rb200_cfg_euler) for the Euler solver
+
+The fused stages round every intermediate exactly where the operator-by-operator evaluation does, so both give the
+same bits (tests/test_full_size_gpu.py compares them).  The VAE (``lda``) and the text encoder run once per image /
+prompt, outside the per-step hot path; they are optional here and any fluxion Chain works.
 """
 
 from __future__ import annotations
@@ -15,7 +26,8 @@ import torch
 from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
-from refiners_b200.foundationals.latent_diffusion.solvers import Solver
+from refiners_b200 import backend as B
+from refiners_b200.foundationals.latent_diffusion.solvers import Euler, ModelPredictionType, Solver
 
 TModel = TypeVar("TModel", bound="LatentDiffusionModel")
 Device = torch.device
@@ -28,65 +40,46 @@ class LatentDiffusionModel(fl.Module, ABC):
         classifier_free_guidance: bool = True, device: Device | str = "cpu", dtype: DType = torch.float32,
     ) -> None:
         super().__init__()
-        self.device: Device = device if isinstance(device, Device) else Device(device)
+        self.device: Device = Device(device) if isinstance(device, str) else device
         self.dtype = dtype
-        self.unet = unet.to(device=self.device, dtype=self.dtype)
-        self.lda = None if lda is None else lda.to(device=self.device, dtype=self.dtype)
-        self.clip_text_encoder = (
-            None if clip_text_encoder is None else clip_text_encoder.to(device=self.device, dtype=self.dtype)
-        )
-        self.solver = solver.to(device=self.device, dtype=self.dtype)
+        place = lambda part: None if part is None else part.to(device=self.device, dtype=self.dtype)  # noqa: E731
+        self.unet = place(unet)
+        self.lda = place(lda)
+        self.clip_text_encoder = place(clip_text_encoder)
+        self.solver = place(solver)
         self.classifier_free_guidance = classifier_free_guidance
-        self._graphed_unet: list[object] = []  # list-wrapped: not a torch sub-module
+        self._graphed_unet: list[Any] = []  # at most one engine.graph.GraphedChain; list-wrapped: not a torch sub-module
 
+    # -- execution engine ---------------------------------------------------------------------------
     def enable_cuda_graph(self, enabled: bool = True) -> None:
-        """Replay the UNet forward from a captured CUDA graph (refiners_b200.engine.graph).
-        The first call after enabling - or after any structural edit - runs the Python walker
-        once under capture; contexts keep being set through the normal API."""
-        for runner in self._graphed_unet:
-            runner.close()  # type: ignore[attr-defined]
-        self._graphed_unet = []
+        """Replay the UNet forward from a captured CUDA graph (refiners_b200.engine.graph.GraphedChain).  The first call
+        after enabling - or after any edit of the tree, a scale or a weight - runs the Python walker once under capture;
+        contexts keep being set through the normal API."""
+        while self._graphed_unet:
+            self._graphed_unet.pop().close()
         if enabled:
             from refiners_b200.engine.graph import GraphedChain
 
-            self._graphed_unet = [GraphedChain(self.unet)]
+            self._graphed_unet.append(GraphedChain(self.unet))
 
     def _run_unet(self, latents: Tensor) -> Tensor:
-        if self._graphed_unet and latents.is_cuda:
-            return self._graphed_unet[0](latents)  # type: ignore[operator]
-        return self.unet(latents)
+        runner = self._graphed_unet[0] if self._graphed_unet and latents.is_cuda else self.unet
+        return runner(latents)
 
-    def set_inference_steps(self, num_steps: int, first_step: int = 0) -> None:
-        self.solver = self.solver.rebuild(num_inference_steps=num_steps, first_inference_step=first_step)
+    def _fused_euler(self, x: Tensor) -> bool:
+        """Whether the prepare / advance stages may run as the two fused launches: plain Euler in noise-prediction mode
+        on CUDA latents of the solver's dtype with the four latent channels only, fusion switched on, no SAG."""
+        solver = self.solver
+        return (
+            type(solver) is Euler
+            and solver.params.model_prediction_type == ModelPredictionType.NOISE
+            and x.is_cuda and x.dtype == solver.sigmas.dtype and solver.sigmas.device == x.device
+            and x.ndim == 4 and x.shape[1] == 4
+            and B.fusion_enabled()
+            and not self.has_self_attention_guidance()
+        )
 
-    @staticmethod
-    def sample_noise(
-        size: tuple[int, ...], device: Device | None = None, dtype: DType | None = None,
-        offset_noise: float | None = None,
-    ) -> Tensor:
-        noise = torch.randn(size=size, device=device, dtype=dtype)
-        if offset_noise is not None:
-            noise += offset_noise * torch.randn(size=(size[0], size[1], 1, 1), device=device, dtype=dtype)
-        return noise
-
-    def init_latents(self, size: tuple[int, int], init_image: Any = None, noise: Tensor | None = None) -> Tensor:
-        height, width = size
-        lh, lw = height // 8, width // 8
-        if noise is None:
-            noise = self.sample_noise(size=(1, 4, lh, lw), device=self.device, dtype=self.dtype)
-        assert list(noise.shape[2:]) == [lh, lw], f"noise shape is not compatible: {noise.shape}, with size: {size}"
-        if init_image is None:
-            latent = noise
-        else:
-            assert self.lda is not None, "image-to-image needs a latent autoencoder (out of the hot path)"
-            encoded = self.lda.image_to_latents(init_image.resize(size=(width, height)))  # type: ignore[attr-defined]
-            latent = self.solver.add_noise(x=encoded, noise=noise, step=self.solver.first_inference_step)
-        return self.solver.scale_model_input(latent, step=-1)
-
-    @property
-    def steps(self) -> list[int]:
-        return self.solver.inference_steps
-
+    # -- the denoising step -----------------------------------------------------------------------------
     @abstractmethod
     def set_unet_context(self, *, timestep: Tensor, clip_text_embedding: Tensor, **_: Tensor) -> None: ...
 
@@ -101,32 +94,68 @@ class LatentDiffusionModel(fl.Module, ABC):
     def forward(
         self, x: Tensor, step: int, *, clip_text_embedding: Tensor, condition_scale: float = 7.5, **kwargs: Tensor,
     ) -> Tensor:
-        cfg = self.classifier_free_guidance
-        if cfg:
+        guided = self.classifier_free_guidance
+        if guided:
             assert clip_text_embedding.shape[0] % 2 == 0, f"invalid batch size: {clip_text_embedding.shape[0]}"
-        timestep = self.solver.timesteps[step].unsqueeze(dim=0)
-        self.set_unet_context(timestep=timestep, clip_text_embedding=clip_text_embedding, **kwargs)
-        latents = torch.cat((x, x)) if cfg else x
-        latents = self.solver.scale_model_input(latents, step=step)
-        if cfg:
-            unconditional, conditional = self._run_unet(latents).chunk(2)
-            predicted_noise = unconditional + condition_scale * (conditional - unconditional)
-            x = x.narrow(dim=1, start=0, length=4)  # > 4 input channels (inpainting) keep 4 latent ones
+        self.set_unet_context(
+            timestep=self.solver.timesteps[step].unsqueeze(dim=0), clip_text_embedding=clip_text_embedding, **kwargs
+        )
+        if self._fused_euler(x):
+            model_input = B.cfg_scale_input(x, self.solver.sigmas, step, twice=guided)
+            return B.cfg_euler(x, self._run_unet(model_input), self.solver.sigmas, step, condition_scale, guided)
+
+        # prepare: with guidance the batch is (unconditional | conditional) copies of the same latents
+        model_input = self.solver.scale_model_input(torch.cat((x, x)) if guided else x, step=step)
+        prediction = self._run_unet(model_input)
+        # advance: only the four latent channels move (an inpainting UNet is fed more)
+        latents = x.narrow(dim=1, start=0, length=4)
+        if guided:
+            unconditional, conditional = prediction.chunk(2)
+            prediction = unconditional + condition_scale * (conditional - unconditional)
             if self.has_self_attention_guidance():
-                predicted_noise += self.compute_self_attention_guidance(
-                    x=x, noise=unconditional, step=step, clip_text_embedding=clip_text_embedding, **kwargs
+                prediction += self.compute_self_attention_guidance(
+                    x=latents, noise=unconditional, step=step, clip_text_embedding=clip_text_embedding, **kwargs
                 )
-        else:
-            predicted_noise = self._run_unet(latents)
-            x = x.narrow(dim=1, start=0, length=4)
-        return self.solver(x, predicted_noise=predicted_noise, step=step)
+        return self.solver(latents, predicted_noise=prediction, step=step)
+
+    # -- bookkeeping around the loop ------------------------------------------------------------------------
+    @property
+    def steps(self) -> list[int]:
+        return self.solver.inference_steps
+
+    def set_inference_steps(self, num_steps: int, first_step: int = 0) -> None:
+        self.solver = self.solver.rebuild(num_inference_steps=num_steps, first_inference_step=first_step)
+
+    @staticmethod
+    def sample_noise(
+        size: tuple[int, ...], device: Device | None = None, dtype: DType | None = None,
+        offset_noise: float | None = None,
+    ) -> Tensor:
+        """Standard normal noise; ``offset_noise`` adds a per-(sample, channel) constant drawn after it."""
+        noise = torch.randn(size=size, device=device, dtype=dtype)
+        if offset_noise is None:
+            return noise
+        per_channel = torch.randn(size=(size[0], size[1], 1, 1), device=device, dtype=dtype)
+        return noise.add_(offset_noise * per_channel)
+
+    def init_latents(self, size: tuple[int, int], init_image: Any = None, noise: Tensor | None = None) -> Tensor:
+        """Starting latents for an image of ``size`` = (height, width) pixels: pure noise, or - image to image - the
+        encoded ``init_image`` noised up to the solver's first inference step; scaled for the solver's first input."""
+        height, width = size
+        latent_hw = [height // 8, width // 8]
+        if noise is None:
+            noise = self.sample_noise(size=(1, 4, *latent_hw), device=self.device, dtype=self.dtype)
+        assert list(noise.shape[2:]) == latent_hw, f"noise shape is not compatible: {noise.shape}, with size: {size}"
+        start = noise
+        if init_image is not None:
+            assert self.lda is not None, "image-to-image needs a latent autoencoder (out of the hot path)"
+            encoded = self.lda.image_to_latents(init_image.resize(size=(width, height)))  # type: ignore[attr-defined]
+            start = self.solver.add_noise(x=encoded, noise=noise, step=self.solver.first_inference_step)
+        return self.solver.scale_model_input(start, step=-1)
 
     def structural_copy(self: TModel) -> TModel:
-        return self.__class__(  # type: ignore[call-arg]
-            unet=self.unet.structural_copy(),
-            lda=None if self.lda is None else self.lda.structural_copy(),
-            clip_text_encoder=None if self.clip_text_encoder is None else self.clip_text_encoder.structural_copy(),
-            solver=self.solver,
-            device=self.device,
-            dtype=self.dtype,
+        twin = lambda part: None if part is None else part.structural_copy()  # noqa: E731
+        return type(self)(  # type: ignore[call-arg]
+            unet=self.unet.structural_copy(), lda=twin(self.lda), clip_text_encoder=twin(self.clip_text_encoder),
+            solver=self.solver, device=self.device, dtype=self.dtype,
         )

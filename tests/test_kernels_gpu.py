@@ -638,3 +638,30 @@ def test_sdpa_growing_maxima(cuda_device, dtype, shape):
         y = B.sdpa(q, k, v, H)
         ref = _sdpa_ref(q.float(), k.float(), v.float(), H)
     assert_close(y, ref, dtype, scale=4.0, what=f"sdpa growing maxima {shape}")
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=str)
+@pytest.mark.parametrize("guided", [True, False], ids=["cfg", "plain"])
+def test_cfg_euler_glue_is_bit_identical_to_the_operator_sequence(cuda_device, dtype, guided):
+    """rb200_cfg_scale_input / rb200_cfg_euler against the reference's operator-by-operator evaluation
+    (model.py:137-159, solvers/euler.py:63-100) on the same device and dtype: the fused launches round every intermediate
+    where the ATen sequence does, so the results are the same bits."""
+    from refiners_b200 import backend as B
+    from refiners_b200.foundationals.latent_diffusion import Euler
+
+    solver = Euler(num_inference_steps=30).to(device=cuda_device, dtype=dtype)
+    x = (_gen((3, 4, 40, 24), 300) * 7.0).to(cuda_device, dtype)
+    eps = _gen((6 if guided else 3, 4, 40, 24), 301).to(cuda_device, dtype)
+    for step, scale in ((0, 5.0), (11, 7.5), (29, 1.3)):
+        with torch.no_grad():
+            want_in = solver.scale_model_input(torch.cat((x, x)) if guided else x, step=step)
+            got_in = B.cfg_scale_input(x, solver.sigmas, step, twice=guided)
+            if guided:
+                u, c = eps.chunk(2)
+                noise = u + scale * (c - u)
+            else:
+                noise = eps
+            want = solver(x, predicted_noise=noise, step=step)
+            got = B.cfg_euler(x, eps, solver.sigmas, step, scale, guided)
+        assert torch.equal(got_in, want_in), f"scale_model_input differs at step {step}: max {(got_in.float() - want_in.float()).abs().max().item():.3e}"
+        assert torch.equal(got, want), f"CFG + Euler update differs at step {step}: max {(got.float() - want.float()).abs().max().item():.3e}"
