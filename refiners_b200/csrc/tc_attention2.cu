@@ -22,7 +22,7 @@
 //   * optionally (POLY) every fourth exponential runs as a Cody-Waite cubic on the FMA pipe instead of MUFU.EX2: at head
 //     dim 64 the exponentials, not the MMAs, bound the kernel (16 MUFU lanes / clk / SM against 4096 MAC / clk / SM).
 //
-// Warps: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-3: idle}; warpgroups 1, 2 = softmax
+// Warps: warpgroup 0 = {warp 0: TMA producer, warp 1: MMA issuer of tile A + TMEM owner, warp 2: MMA issuer of tile B, warp 3: idle}; warpgroups 1, 2 = softmax
 // of query tile A (key columns 0-63 / 64-127); warpgroups 3, 4 = softmax of query tile B.  thread = (query row = TMEM
 // lane, column half).
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
@@ -110,11 +110,11 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     prefetch_tmap(&map_v);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&kv_empty[s], 2);   // both MMA issuers release a K/V stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
-      mbar_init(&q_empty[b], 1);
+      mbar_init(&q_empty[b], 2);
       mbar_init(&bar_s[b], 1);
       mbar_init(&bar_sfree[b], 8);   // 2 column halves x 4 warps
       mbar_init(&bar_p[b], 8);
@@ -158,71 +158,72 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
       // ================================================================================ MMA
+      // One issuing thread PER query tile (warp 1: tile A, warp 2: tile B).  Everything an issuer does is a chain of
+      // latencies - mbarrier try_wait (~90 cycles even when the phase has completed), tcgen05 fence, descriptor set-up,
+      // MMA issue, commit - about 2000 cycles per key tile when a single thread served both tiles: with one thread the
+      // softmax warps spent 27 % of their time waiting for S tiles and P V completions while the tensor pipe was 21 %
+      // busy (ncu, profiles/r02_ncu_attn_*).  tcgen05.commit tracks the MMAs of the committing thread only, so the two
+      // issuers need no coordination beyond the K/V and Q slots, which are released when BOTH have committed (count 2).
       if (lane == 0) {
-        int st_k = 0, st_v = 0;     // ring cursors: stage whose K feeds the next S pair / whose V feeds the next P V pair
+        const int g = warp - 1;
+        int st_k = 0, st_v = 0;     // ring cursors: stage whose K feeds the next S tile / whose V feeds the next P V
         uint32_t ph_k = 0;
-        uint32_t t[2] = {0, 0};     // tiles issued per group so far (barrier phases of bar_s / bar_p / bar_o / bar_sfree)
+        uint32_t t = 0;             // P V tiles issued so far (phases of bar_p / bar_o)
+        uint32_t s_issued = 0;      // S tiles issued so far (runs one ahead of t)
         uint32_t n = 0;
-        // S_g(tile) = Q_g K^T: the K stage must have landed (checked once per tile by the caller) and the group must have
-        // read its previous S tile out of TMEM
-        auto issue_s = [&](int g, uint32_t qb, int stage_k, uint32_t tiles_done) {
-          if (tiles_done > 0) mbar_wait(&bar_sfree[g], (tiles_done - 1) & 1, 4);
+        const uint32_t tmem_s = tmem_base + g * 128, tmem_o = tmem_base + 256 + g * 64;
+        const uint32_t pbase = smem_u32(sP + g * P_BYTES);
+        // S_g(tile) = Q_g K^T: the group must have read its previous S tile out of TMEM (it releases the tile as soon as the
+        // values sit in its registers, early in its work on that tile)
+        auto issue_s = [&](uint32_t qb, int stage_k) {
+          if (s_issued > 0) mbar_wait(&bar_sfree[g], (s_issued - 1) & 1, 4);
+          ++s_issued;
           tcgen05_fence_after();
           const uint64_t dq = desc_kmajor(smem_u32(sQ + qb * Q_BYTES + g * Q_TILE_BYTES));
           const uint64_t dk = desc_kmajor(smem_u32(sK + stage_k * K_BYTES));
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base + g * 128, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
+          for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dk + uint64_t(k * 2), p.idesc_qk, k > 0);
           umma_commit(&bar_s[g]);
         };
-        uint32_t s_issued[2] = {0, 0};  // S tiles issued per group (runs one ahead of t[g])
-        for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
-          const uint32_t qb = n & 1, qph = (n >> 1) & 1;
-          mbar_wait(&q_full[qb], qph, 5);
-          mbar_wait(&kv_full[st_k], ph_k, 3);
-          issue_s(0, qb, st_k, s_issued[0]++);
-          issue_s(1, qb, st_k, s_issued[1]++);
+        auto next_k = [&]() {
           if (++st_k == STAGES) {
             st_k = 0;
             ph_k ^= 1;
           }
+        };
+        for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
+          const uint32_t qb = n & 1, qph = (n >> 1) & 1;
+          mbar_wait(&q_full[qb], qph, 5);
+          mbar_wait(&kv_full[st_k], ph_k, 3);
+          issue_s(qb, st_k);
+          next_k();
           for (int j = 0; j < p.ntiles; ++j) {
-            // S_g(j + 1) FIRST: a softmax group releases its S tile as soon as the values sit in its registers (early in
-            // tile j), so the next S can be computed while the group is still exponentiating - when it comes back for
-            // tile j + 1 the logits are already waiting in TMEM.  (Issuing S_g(j + 1) after P_g V(j), as the first version of
-            // this kernel did, put two MMA latencies on every group's critical path and let both groups fall into lock
-            // step: 4600 cycles per key tile instead of the ~2100 the exponentials need.)
+            // S(j + 1) FIRST: it only needs the S tile to be free, which happens long before P(j) is ready - when the
+            // group comes back for tile j + 1 the logits are already waiting in TMEM
             if (j + 1 < p.ntiles) {
               mbar_wait(&kv_full[st_k], ph_k, 6);  // K_{j+1}
-              issue_s(0, qb, st_k, s_issued[0]++);
-              issue_s(1, qb, st_k, s_issued[1]++);
-              if (++st_k == STAGES) {
-                st_k = 0;
-                ph_k ^= 1;
-              }
+              issue_s(qb, st_k);
+              next_k();
             }
+            mbar_wait(&bar_p[g], t & 1, 7);  // P(j) is in smem; O has been rescaled if it had to be
+            if (j == 0 && n > 0) mbar_wait(&bar_ofree[g], (n - 1) & 1, 8);  // O still holds the previous work item until read out
+            tcgen05_fence_after();
+            const uint32_t vbase = smem_u32(sV + st_v * V_BYTES);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              mbar_wait(&bar_p[g], t[g] & 1, 7);  // P_g(j) is in smem; O_g has been rescaled if it had to be
-              if (j == 0 && n > 0) mbar_wait(&bar_ofree[g], (n - 1) & 1, 8);  // O_g still holds the previous work item until read out
-              tcgen05_fence_after();
-              const uint32_t pbase = smem_u32(sP + g * P_BYTES);
-              const uint32_t vbase = smem_u32(sV + st_v * V_BYTES);
-#pragma unroll
-              for (int k = 0; k < KT / 16; ++k) {
-                // A = P (K-major, two 64-key slabs; +32 B per 16 keys inside a swizzle row); B = V (MN-major: +16 key rows * 128 B)
-                const uint64_t dp = desc_kmajor(pbase + (k >> 2) * P_SLAB) + uint64_t((k & 3) * 2);
-                const uint64_t dv = desc_mnmajor(vbase, V_BYTES) + uint64_t(k * 128);
-                umma_f16(tmem_base + 256 + g * 64, dp, dv, p.idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-              }
-              if (g == 1) umma_commit(&kv_empty[st_v]);  // both groups' P V (and, earlier, both S) have consumed this stage
-              umma_commit(&bar_o[g]);
-              ++t[g];
+            for (int k = 0; k < KT / 16; ++k) {
+              // A = P (K-major, two 64-key slabs; +32 B per 16 keys inside a swizzle row); B = V (MN-major: +16 key rows * 128 B)
+              const uint64_t dp = desc_kmajor(pbase + (k >> 2) * P_SLAB) + uint64_t((k & 3) * 2);
+              const uint64_t dv = desc_mnmajor(vbase, V_BYTES) + uint64_t(k * 128);
+              umma_f16(tmem_o, dp, dv, p.idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
             }
+            umma_commit(&kv_empty[st_v]);  // this issuer's S (issued earlier) and P V have consumed the stage; count 2
+            umma_commit(&bar_o[g]);
+            ++t;
             if (++st_v == STAGES) st_v = 0;
           }
-          umma_commit(&q_empty[qb]);  // every MMA reading this Q buffer has been issued; it frees when they retire
+          umma_commit(&q_empty[qb]);  // every MMA of this issuer reading the Q buffer has been issued; count 2
         }
       }
     }
