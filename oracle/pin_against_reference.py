@@ -208,6 +208,41 @@ def pin_dinov2(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'dinov2.safetensors'}")
 
 
+def pin_clip(write: bool) -> None:
+    """CLIP vision towers (clip/image_encoder.py): ViT-H/14 - the IP-Adapter's image encoder (d = 80, 257 tokens) - and a
+    tiny configuration (d = 16, 17 tokens), keyed weights, own fixture file."""
+    _import_reference()
+    from refiners.foundationals.clip.image_encoder import CLIPImageEncoder, CLIPImageEncoderH
+    from safetensors.torch import save_file
+
+    from oracle import clip as oclip
+    from oracle.cases import keyed_input
+    from oracle.weights import keyed_state_dict
+
+    print("CLIP image encoders")
+    fx = {}
+    with torch.no_grad():
+        big = CLIPImageEncoderH()
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in big.state_dict().items()}, seed=9)
+        big.load_state_dict(sd)
+        x = keyed_input("clip.h.image", (2, 3, 224, 224))
+        y = big(x)
+        _close("CLIPImageEncoderH", oclip.image_encoder(sd, x, patch_size=14, num_layers=32, num_heads=16), y, rel=2e-5)
+        fx["h.y"] = y
+        tiny_cfg = dict(image_size=32, embedding_dim=32, output_dim=16, patch_size=8, num_layers=2, num_attention_heads=2, feedforward_dim=64)
+        tiny = CLIPImageEncoder(**tiny_cfg)
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in tiny.state_dict().items()}, seed=10)
+        tiny.load_state_dict(sd)
+        x = keyed_input("clip.tiny.image", (3, 3, 32, 32))
+        y = tiny(x)
+        _close("CLIPImageEncoder tiny", oclip.image_encoder(sd, x, patch_size=8, num_layers=2, num_heads=2), y)
+        fx["tiny.y"] = y
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "clip.safetensors"))
+        print(f"  wrote {GOLDEN / 'clip.safetensors'}")
+
+
 def pin_full_size(write: bool) -> None:
     """BASELINE-size cases (oracle/cases.py): SDXLUNet at 128x128 latents plain (config 2), with 700 LoRA
     adapters + IP-Adapter (config 3), with ControlLora (config 4), one full StableDiffusion_XL step with CFG +
@@ -536,6 +571,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-dinov2": pin_dinov2,
+        "--only-clip": pin_clip,
         "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]

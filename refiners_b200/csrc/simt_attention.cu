@@ -1,5 +1,5 @@
-// Generic flash-style attention on CUDA cores: any head dim <= 256, any sequence lengths, any
-// dtype.  It is the correctness anchor for the tcgen05 kernel and the path for shapes that
+// Generic flash-style attention on CUDA cores: any head dim <= 512 (the VAE bottleneck's single 512-wide head,
+// latent_diffusion/auto_encoder.py:175 of the reference), any sequence lengths, any dtype.  It is the correctness anchor for the tcgen05 kernel and the path for shapes that
 // kernel does not take.  Optional second key/value set (IP-Adapter): two independent
 // softmaxes, o = A(q,k,v) + scale2 * A(q,k2,v2).
 #include "common.cuh"
@@ -7,9 +7,9 @@
 namespace rb200 {
 namespace {
 
-constexpr int QT = 32, KT = 32, NT = 128, DMAX = 256, DPT = DMAX / 4;
+constexpr int QT = 32, KT = 32, NT = 128, DMAX = 512;  // DPT = output columns per thread: 64 (D <= 256) or 128
 
-template <typename T>
+template <typename T, int DPT>
 __global__ void __launch_bounds__(NT) simt_sdpa_kernel(const SdpaProblem p) {
   extern __shared__ float sm[];
   const int D = p.D;
@@ -132,15 +132,21 @@ __global__ void __launch_bounds__(NT) simt_sdpa_kernel(const SdpaProblem p) {
   }
 }
 
-template <typename T>
-int launch(cudaStream_t st, const SdpaProblem& p) {
+template <typename T, int DPT>
+int launch_dpt(cudaStream_t st, const SdpaProblem& p) {
   const size_t smem = sizeof(float) * (size_t(QT) * p.D + size_t(KT) * (p.D + 1) + size_t(KT) * p.D + size_t(QT) * (KT + 1));
-  if (smem > 48 * 1024) cudaFuncSetAttribute(simt_sdpa_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(simt_sdpa_kernel<T, DPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+    RB200_FAIL(-2, "simt_sdpa: cannot reserve %zu bytes of shared memory (head dim %d)", smem, p.D);
   if (p.B > 65535 || p.H > 65535) RB200_FAIL(-1, "sdpa: batch/heads too large for one launch");
   dim3 grid((unsigned)ceil_div(p.Sq, QT), (unsigned)p.H, (unsigned)p.B);
-  simt_sdpa_kernel<T><<<grid, NT, smem, st>>>(p);
+  simt_sdpa_kernel<T, DPT><<<grid, NT, smem, st>>>(p);
   RB200_CHECK_LAUNCH("simt_sdpa");
   return 0;
+}
+
+template <typename T>
+int launch(cudaStream_t st, const SdpaProblem& p) {
+  return p.D <= 256 ? launch_dpt<T, 64>(st, p) : launch_dpt<T, 128>(st, p);
 }
 
 }  // namespace

@@ -5,10 +5,10 @@ Module trees and state-dict keys are those of the reference's
 `LatentDiffusionAutoencoder` :282-413); ``tests/test_reference_structure.py`` compares them node by node and
 ``tests/golden/vae.safetensors`` pins encode / decode against the reference's outputs.
 
-Status: host path complete (tensor API: ``encode`` / ``decode`` and the PIL helpers).  On a GPU every
-conv / GroupNorm(+SiLU) of the VAE already runs through ``librefiners_b200.so``; the single-head
-attention of the 512-channel bottleneck has head dim 512, beyond the attention kernels' d <= 256, so a CUDA
-``decode`` raises until that variant lands.  Tiled inference (:415-621 in the reference) is not built.
+Status: ``encode`` / ``decode`` and the PIL helpers run on the host and on the GPU (every conv, GroupNorm(+SiLU) and
+residual add through ``librefiners_b200.so``; the single 512-wide attention head of the bottleneck runs on the CUDA-core
+flash kernel, which takes head dims up to 512 - it executes once per image, not per denoising step; GPU parity in
+tests/test_models_golden.py::test_vae_gpu).  Tiled inference (:415-621 in the reference) is not built.
 """
 
 from __future__ import annotations

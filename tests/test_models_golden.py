@@ -278,6 +278,21 @@ def test_sd1_controlnet_host():
 # ------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_vae_gpu(cuda_device, dtype):
+    """LatentDiffusionAutoencoder.encode / decode on the kernels (the bottleneck attention has ONE head of dim 512)."""
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+
+    f = load_file(str(GOLDEN / "vae.safetensors"))
+    lda = LatentDiffusionAutoencoder(device="meta")
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in lda.state_dict().items()}, seed=5)
+    lda.load_state_dict({k: v.to(cuda_device, dtype) for k, v in sd.items()}, assign=True)
+    with no_grad():
+        check(lda.decode(f["vae.z"].to(cuda_device, dtype)), f["vae.decoded"], dtype)
+        check(lda.encode(f["vae.image"].to(cuda_device, dtype)), f["vae.encoded"], dtype)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
 def test_sd1_controlnet_gpu(cuda_device, dtype):
     f = load_file(str(GOLDEN / "controlnet.safetensors"))
     unet, adapter = load_controlnet_unet(device=cuda_device, dtype=dtype)

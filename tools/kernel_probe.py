@@ -78,6 +78,16 @@ elif which in ("attn", "attn4096"):
     q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
     k, v = torch.randn_like(q), torch.randn_like(q)
     fn, flops = (lambda: B.sdpa(q, k, v, H)), 4.0 * Bn * H * S * S * 64
+elif which == "gn":  # GroupNorm + SiLU on the largest UNet map: 16 x 320 x 128 x 128
+    x = torch.randn(16, 320, 128, 128, device=dev, dtype=bf).contiguous(memory_format=torch.channels_last)
+    g, b = torch.ones(320, device=dev, dtype=bf), torch.zeros(320, device=dev, dtype=bf)
+    fn, flops = (lambda: B.group_norm(x, 32, g, b, 1e-5, silu=True)), 0.0
+    nbytes = x.numel() * 2 * 3  # read twice (statistics, apply) + write once
+elif which == "ln":  # LayerNorm of the 1280-wide transformer blocks: [16, 1024, 1280]
+    x = torch.randn(16, 1024, 1280, device=dev, dtype=bf)
+    g, b = torch.ones(1280, device=dev, dtype=bf), torch.zeros(1280, device=dev, dtype=bf)
+    fn, flops = (lambda: B.layer_norm(x, g, b, 1e-5)), 0.0
+    nbytes = x.numel() * 2 * 2
 else:
     raise SystemExit(f"unknown probe {which}")
 
@@ -95,4 +105,7 @@ with torch.no_grad():
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
 ms = sorted(times)[len(times) // 2]
-print(f"{which}: median {ms * 1e3:.1f} us, {flops / ms / 1e9:.1f} TFLOP/s ({flops / 1e9:.1f} GFLOP per launch)")
+if flops:
+    print(f"{which}: median {ms * 1e3:.1f} us, {flops / ms / 1e9:.1f} TFLOP/s ({flops / 1e9:.1f} GFLOP per launch)")
+else:
+    print(f"{which}: median {ms * 1e3:.1f} us, {nbytes / ms / 1e6:.0f} GB/s ({nbytes / 1e6:.1f} MB algorithmic per launch)")
