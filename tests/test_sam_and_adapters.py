@@ -250,3 +250,34 @@ def test_lora_block_gpu(cuda_device, dtype, fusion):
         B.set_fusion(prev)
         B.set_lora_merge(prev_merge)
     assert launches > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+@pytest.mark.parametrize("stride", [1, 2])
+def test_conv2d_lora_gpu(cuda_device, dtype, stride):
+    """LoraAdapter around a Conv2d with a Conv2dLora (1x1 down with the target's stride, 3x3 up; lora.py:269-380 of the
+    reference): every conv of the Sum runs on the kernels; checked against y = conv(x) + s * up(down(x)) in fp32."""
+    import torch.nn.functional as F
+
+    from refiners_b200 import backend as B
+    from refiners_b200.fluxion.adapters import Conv2dLora
+
+    torch.manual_seed(11)
+    conv = fl.Conv2d(64, 96, kernel_size=3, stride=stride, padding=1)
+    holder = fl.Chain(conv)
+    lora = Conv2dLora("c", in_channels=64, out_channels=96, rank=8, scale=1.3)
+    lora.up.weight.data.normal_(0, 0.05)
+    adapter = LoraAdapter(conv, lora)
+    assert lora.is_compatible(conv) and tuple(lora.down.stride) == (stride, stride)
+    adapter.inject(holder)
+    x = torch.randn(2, 64, 16, 16)
+    rd = lambda t: t.detach().to(dtype).float()  # what the kernels see
+    ref = F.conv2d(rd(x), rd(conv.weight), rd(conv.bias), stride=stride, padding=1) + 1.3 * F.conv2d(
+        F.conv2d(rd(x), rd(lora.down.weight), None, stride=stride), rd(lora.up.weight), None, padding=1)
+    holder = holder.to(cuda_device, dtype)
+    before = B.launch_count()
+    with no_grad():
+        y = holder(x.to(cuda_device, dtype))
+    assert B.launch_count() - before >= 3  # base conv, down, up (+ scale / add)
+    check(y, ref, dtype)
