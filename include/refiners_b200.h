@@ -197,6 +197,17 @@ int rb200_sdpa(void* stream, int dtype, const void* q, const void* k, const void
                float scale, int is_causal, const void* k2, const void* v2, int64_t Sk2,
                int64_t k2_sb, int64_t k2_ss, int64_t v2_sb, int64_t v2_ss, float scale2);
 
+/* ---- attention probabilities (self-attention guidance) ----------------------------------------
+ * Replaces foundationals/latent_diffusion/self_attention_guidance.py:42-47
+ * (SelfAttentionMap.compute_attention_scores):
+ *   probs[b, h, i, j] = softmax_j( q[b, i, h*D:(h+1)*D] . k[b, j, h*D:(h+1)*D] * scale )
+ * q: [B, Sq, H*D] with element strides (q_sb, q_ss), k likewise; probs: contiguous [B, H, Sq, Sk].
+ * D % 8 == 0 (fp32: % 4), D <= 256, rows 16-byte aligned.  Logits and the softmax are fp32, the
+ * stored probabilities are rounded once to `dtype`. */
+int rb200_attention_probs(void* stream, int dtype, const void* q, const void* k, void* probs, int64_t B,
+                          int H, int64_t Sq, int64_t Sk, int D, int64_t q_sb, int64_t q_ss,
+                          int64_t k_sb, int64_t k_ss, float scale);
+
 /* ---- SAM decomposed relative-position attention ---------------------------------------------
  * Replaces foundationals/segment_anything/image_encoder.py:87-127 (RelativePositionAttention):
  *   logits = (q * d^-1/2) k^T + rel_h[:, :, None] + rel_w[:, None, :], softmax, @ v

@@ -141,6 +141,46 @@ def pin_denoise_step(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'step.safetensors'}")
 
 
+def pin_sag(write: bool) -> None:
+    """Self-attention guidance: one StableDiffusion_1 step (DDIM, CFG, SAG scale 0.75) on 64x64 latents with keyed
+    weights (middle block 8x8 = 64 tokens), the recorded mask included; own generator and fixture file."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.solvers import DDIM
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.model import StableDiffusion_1
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+    from safetensors.torch import save_file
+
+    from oracle import sag as osag
+    from oracle import unet as ounet
+    from oracle.weights import keyed_state_dict
+
+    print("StableDiffusion_1 step with self-attention guidance (DDIM)")
+    gen = torch.Generator().manual_seed(2210)
+    g = lambda *s: torch.randn(*s, generator=gen)
+    with torch.no_grad():
+        unet = SD1UNet(4)
+        sdict = keyed_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=1)
+        unet.load_state_dict(sdict)
+        sd = StableDiffusion_1(unet=unet, solver=DDIM(num_inference_steps=30))
+        sd.set_self_attention_guidance(enable=True, scale=0.75)
+        x, ctx = g(2, 4, 64, 64), g(4, 77, 768)
+        fx = {"sag.x": x, "sag.ctx": ctx}
+        schedule = osag.DDIMSchedule(30)
+        _close("DDIM timesteps", schedule.timesteps.float(), sd.solver.timesteps.float())
+        run = lambda lat, ts, guided: ounet.sd1_unet(sdict, lat, ts, ctx if guided else ctx.chunk(2)[0])  # noqa: E731
+        for step, scale in ((3, 7.5), (20, 5.0)):
+            y = sd(x, step=step, clip_text_embedding=ctx, condition_scale=scale)
+            fx[f"sag.y_{step}"] = y
+            _close(f"SAG step {step} (scale {scale})", osag.denoise_step(run, schedule, x, step, scale, 0.75), y)
+        sd.set_self_attention_guidance(enable=False)
+        plain = sd(x, step=3, clip_text_embedding=ctx, condition_scale=7.5)
+        print(f"  guidance moves the step-3 result by {float((fx['sag.y_3'] - plain).abs().max()):.3e} (max |y| {float(plain.abs().max()):.3f})")
+    if write:
+        GOLDEN.mkdir(parents=True, exist_ok=True)
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "sag.safetensors"))
+        print(f"  wrote {GOLDEN / 'sag.safetensors'}")
+
+
 def pin_vae(write: bool) -> None:
     """LatentDiffusionAutoencoder.encode / decode (auto_encoder.py:305-331) on keyed weights; own fixture file."""
     _import_reference()
@@ -571,7 +611,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-dinov2": pin_dinov2,
-        "--only-clip": pin_clip,
+        "--only-clip": pin_clip, "--only-sag": pin_sag,
         "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]

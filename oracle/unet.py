@@ -74,11 +74,21 @@ def residual_block(sd: SD, prefix: str, x: Tensor, temb: Tensor, eps: float = 1e
     return h + shortcut
 
 
+# Self-attention guidance probes (self_attention_guidance.py:22-59, placed by stable_diffusion_1/ and
+# stable_diffusion_xl/self_attention_guidance.py:20-31): when ``middle_probe`` is a dict, a UNet pass leaves in it the
+# middle block's feature-map size ("shape") and the attention probabilities of its FIRST self-attention ("map").
+middle_probe: dict | None = None
+
+
 def attention(sd: SD, prefix: str, q_in: Tensor, kv_in: Tensor, heads: int) -> Tensor:
     """fl.Attention: Distribute(Wq, Wk, Wv) -> SDPA -> Wo  (fluxion/layers/attentions.py:205-316)."""
     q = _lin(sd, prefix + ".Distribute.Linear_1", q_in)
     k = _lin(sd, prefix + ".Distribute.Linear_2", kv_in)
     v = _lin(sd, prefix + ".Distribute.Linear_3", kv_in)
+    if middle_probe is not None and "MiddleBlock" in prefix and prefix.endswith(".SelfAttention") and "map" not in middle_probe:
+        split = lambda t: t.reshape(t.shape[0], t.shape[1], heads, -1).transpose(1, 2)  # noqa: E731
+        qh, kh = split(q), split(k)
+        middle_probe["map"] = torch.softmax(qh @ kh.transpose(-1, -2) / qh.shape[-1] ** 0.5, dim=-1)
     o = ops.sdpa(q, k, v, heads)
     ip = getattr(sd, "ip", None)
     if ip and prefix in ip:
@@ -106,6 +116,8 @@ def cross_attention_2d(sd: SD, prefix: str, x: Tensor, context: Tensor, heads: i
     """cross_attention.py:92-175: GN(eps 1e-6) -> project in -> [B, HW, C] -> N blocks -> project out,
     residual around everything.  SDXL projects with Linear, SD1.5 with 1x1 conv."""
     B, C, H, W = x.shape
+    if middle_probe is not None and "MiddleBlock" in prefix:
+        middle_probe["shape"] = (H, W)
     c1, c2, c3 = prefix + ".Chain_1", prefix + ".Chain_2", prefix + ".Chain_3"
     h = ops.group_norm(x, 32, sd[c1 + ".GroupNorm.weight"], sd[c1 + ".GroupNorm.bias"], 1e-6)
     if linear_proj:

@@ -92,6 +92,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_add": (_I, [_P, _I, _P, _P, _P, _L, _F]),
     "rb200_cfg_scale_input": (_I, [_P, _I, _P, _P, _L, _P, _I]),
     "rb200_cfg_euler": (_I, [_P, _I, _P, _P, _P, _L, _P, _F, _I]),
+    "rb200_attention_probs": (_I, [_P, _I, _P, _P, _P, _L, _I, _L, _L, _I, _L, _L, _L, _L, _F]),
     "rb200_sdpa": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _L, _L, _I] + [_L] * 8 + [_F, _I, _P, _P, _L] + [_L] * 4 + [_F]),
     "rb200_sam_attention_workspace_bytes": (_Z, [_L, _I, _I, _I, _I]),
     "rb200_sam_attention": (_I, [_P, _I, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _Z]),
@@ -1094,6 +1095,24 @@ def sdpa(
 ) -> Tensor:
     _inference_only(q, k, v)
     return _ops.sdpa(q, k, v, k2, v2, num_heads, is_causal, scale2)
+
+
+def attention_probs(q: Tensor, k: Tensor, num_heads: int) -> Tensor:
+    """``softmax(q k^T / sqrt(d))`` as a ``[B, heads, Sq, Sk]`` tensor (self-attention guidance); see rb200_attention_probs."""
+    _inference_only(q, k)
+    _same(q, k)
+    lib = load_library()
+    B, Sq, C = q.shape
+    if C % num_heads or k.shape[0] != B or k.shape[2] != C:
+        raise BackendError(f"attention_probs: bad shapes q{tuple(q.shape)} k{tuple(k.shape)} heads={num_heads}")
+    D, Sk = C // num_heads, k.shape[1]
+    q, k = _rows(q), _rows(k)
+    probs = torch.empty((B, num_heads, Sq, Sk), device=q.device, dtype=q.dtype)
+    if probs.numel():
+        with torch.cuda.device(q.device):
+            _check(lib.rb200_attention_probs(_stream(), _dtype_code(q), q.data_ptr(), k.data_ptr(), probs.data_ptr(), B, num_heads, Sq, Sk, D,
+                                             q.stride(0), q.stride(1), k.stride(0), k.stride(1), float(D) ** -0.5))
+    return probs
 
 
 def sam_attention(qkv: Tensor, rel_h: Tensor, rel_w: Tensor, num_heads: int) -> Tensor:

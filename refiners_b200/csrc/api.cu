@@ -57,6 +57,9 @@ int resize_nearest_impl(cudaStream_t, int, const void*, void*, int64_t, int, int
 int conv_pack_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int, int);
 int geglu_pack_impl(cudaStream_t, int, const void*, const void*, void*, void*, int64_t, int64_t);
 int lora_pack_impl(cudaStream_t, int, int, const rb200_lora*, int64_t, int64_t, void*, void*, float*, int);
+// implemented in attn_probs.cu
+int attention_probs_impl(cudaStream_t, int, const void*, const void*, void*, int64_t, int, int64_t, int64_t, int, int64_t, int64_t, int64_t, int64_t,
+                         float);
 // implemented in sam_attention.cu
 int sam_attention_impl(cudaStream_t, int, const void*, const void*, const void*, void*, int64_t, int, int, int, int, void*, size_t);
 size_t sam_attention_ws(int64_t, int, int, int, int);
@@ -282,6 +285,14 @@ int rb200_sdpa(void* stream, int dtype, const void* q, const void* k, const void
     if (tc_sdpa_supported(p)) return tc_sdpa(st, p);
   }
   return simt_sdpa(st, p);
+}
+
+int rb200_attention_probs(void* stream, int dtype, const void* q, const void* k, void* probs, int64_t B, int H, int64_t Sq, int64_t Sk, int D,
+                          int64_t q_sb, int64_t q_ss, int64_t k_sb, int64_t k_ss, float scale) {
+  if (bad_dtype(dtype) || !q || !k || !probs) RB200_FAIL(-1, "attention_probs: bad arguments");
+  if (H <= 0 || D <= 0 || Sk <= 0 || Sq < 0) RB200_FAIL(-1, "attention_probs: bad shape");
+  if (B <= 0 || Sq == 0) return 0;
+  return attention_probs_impl(static_cast<cudaStream_t>(stream), dtype, q, k, probs, B, H, Sq, Sk, D, q_sb, q_ss, k_sb, k_ss, scale);
 }
 
 size_t rb200_sam_attention_workspace_bytes(int64_t Bw, int Hh, int Ww, int heads, int d) { return sam_attention_ws(Bw, Hh, Ww, heads, d); }

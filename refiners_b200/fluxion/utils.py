@@ -2,7 +2,7 @@
 
 Covers the subset of /root/reference/src/refiners/fluxion/utils.py that the hot
 path touches (seed, no_grad, pad, interpolate, tensor summary for ChainError,
-safetensors IO). Image helpers live outside the denoising path and are not mirrored.
+safetensors IO, PIL <-> tensor, the Gaussian blur of self-attention guidance).
 """
 
 from pathlib import Path
@@ -32,6 +32,35 @@ def pad(x: Tensor, pad: Iterable[int], value: float = 0.0, mode: str = "constant
 
 def interpolate(x: Tensor, size: torch.Size, mode: str = "nearest", antialias: bool = False) -> Tensor:
     return F.interpolate(x, size=tuple(size), mode=mode, antialias=antialias)
+
+
+def gaussian_blur(
+    tensor: Tensor, kernel_size: int | tuple[int, int], sigma: float | tuple[float, float] | None = None
+) -> Tensor:
+    """Depthwise Gaussian blur of the last two axes with reflected borders (reference utils.py:65-113, the
+    torchvision recipe): normalised 1-D taps on ``[-(k-1)/2, (k-1)/2]``, their outer product as ONE 2-D kernel per
+    channel, ``sigma`` defaulting to ``0.15 k + 0.35``.  ``kernel_size`` / ``sigma`` pairs are (x, y)."""
+    assert torch.is_floating_point(tensor)
+    sizes = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    if sigma is None:
+        sigmas: tuple[float, ...] = tuple(0.15 * k + 0.35 for k in sizes)
+    elif isinstance(sigma, float):
+        sigmas = (sigma, sigma)
+    else:
+        assert isinstance(sigma, tuple)
+        sigmas = sigma
+
+    def taps(k: int, s: float) -> Tensor:
+        reach = 0.5 * (k - 1)
+        grid = torch.linspace(-reach, reach, steps=k, device=tensor.device, dtype=tensor.dtype)
+        bell = torch.exp(-0.5 * (grid / s).pow(2))
+        return bell / bell.sum()
+
+    (kx, ky), (sx, sy) = sizes, sigmas
+    window = torch.mm(taps(ky, sy)[:, None], taps(kx, sx)[None, :])
+    channels = tensor.shape[-3]
+    framed = pad(tensor, (kx // 2, kx // 2, ky // 2, ky // 2), mode="reflect")
+    return F.conv2d(framed, weight=window.expand(channels, 1, ky, kx), groups=channels)
 
 
 def summarize_tensor(tensor: Tensor, /) -> str:

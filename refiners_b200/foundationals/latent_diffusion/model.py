@@ -63,7 +63,9 @@ class LatentDiffusionModel(fl.Module, ABC):
             self._graphed_unet.append(GraphedChain(self.unet))
 
     def _run_unet(self, latents: Tensor) -> Tensor:
-        runner = self._graphed_unet[0] if self._graphed_unet and latents.is_cuda else self.unet
+        # self-attention guidance reads what the walker's probes record on every pass: it runs the walker itself
+        graphed = self._graphed_unet and latents.is_cuda and not self.has_self_attention_guidance()
+        runner = self._graphed_unet[0] if graphed else self.unet
         return runner(latents)
 
     def _fused_euler(self, x: Tensor) -> bool:
@@ -83,13 +85,64 @@ class LatentDiffusionModel(fl.Module, ABC):
     @abstractmethod
     def set_unet_context(self, *, timestep: Tensor, clip_text_embedding: Tensor, **_: Tensor) -> None: ...
 
+    # -- self-attention guidance (arXiv:2210.00939) ----------------------------------------------------------
+    def _sag_adapter_type(self) -> type[Any] | None:
+        """The SAG adapter class of this model family (None: the family has none)."""
+        return None
+
+    def _find_sag_adapter(self) -> Any:
+        kind = self._sag_adapter_type()
+        if kind is None:
+            return None
+        return next((parent for parent in self.unet.get_parents() if isinstance(parent, kind)), None)
+
     def has_self_attention_guidance(self) -> bool:
-        return False
+        return self._find_sag_adapter() is not None
+
+    def set_self_attention_guidance(self, enable: bool, scale: float = 1.0) -> None:
+        """Inject (or re-scale) / eject the family's SAG adapter around the UNet."""
+        adapter = self._find_sag_adapter()
+        if not enable:
+            if adapter is not None:
+                adapter.eject()
+        elif adapter is not None:
+            adapter.scale = scale
+        else:
+            kind = self._sag_adapter_type()
+            assert kind is not None, f"{type(self).__name__} has no self-attention guidance adapter"
+            kind(target=self.unet, scale=scale).inject()
+
+    def _unconditional_half(self, *, clip_text_embedding: Tensor, **kwargs: Tensor) -> dict[str, Tensor]:
+        """The conditioning of the guidance pass: the unconditional half of whatever is batched (uncond | cond)."""
+        return {"clip_text_embedding": clip_text_embedding.chunk(2)[0], **kwargs}
 
     def compute_self_attention_guidance(
         self, x: Tensor, noise: Tensor, step: int, *, clip_text_embedding: Tensor, **kwargs: Tensor,
     ) -> Tensor:
-        raise NotImplementedError("self-attention guidance is out of the hot-path scope (SURVEY.md section 2 #18)")
+        """``scale * (noise - unet(degraded latents))`` where the degraded latents are ``x`` blurred where the middle
+        block attends (the probes recorded that during the pass that produced ``noise``), and the extra UNet pass is
+        unconditional: half the batch, half of every batched context (reference stable_diffusion_1/model.py:175-213,
+        stable_diffusion_xl/model.py:194-250)."""
+        adapter = self._find_sag_adapter()
+        assert adapter is not None
+        degraded = adapter.compute_degraded_latents(
+            solver=self.solver, latents=x, noise=noise, step=step, classifier_free_guidance=True
+        )
+        self.set_unet_context(
+            timestep=self.solver.timesteps[step].unsqueeze(dim=0),
+            **self._unconditional_half(clip_text_embedding=clip_text_embedding, **kwargs),
+        )
+        if "ip_adapter" not in self.unet.provider.contexts:
+            return adapter.scale * (noise - self.unet(degraded))
+        # an injected IP-Adapter keeps its (uncond | cond) image embedding in a context of its own: halve it for this
+        # pass and put the full one back
+        image_prompt = self.unet.use_context("ip_adapter")
+        full = image_prompt["clip_image_embedding"]
+        image_prompt["clip_image_embedding"] = full.chunk(2)[0]
+        try:
+            return adapter.scale * (noise - self.unet(degraded))
+        finally:
+            image_prompt["clip_image_embedding"] = full
 
     def forward(
         self, x: Tensor, step: int, *, clip_text_embedding: Tensor, condition_scale: float = 7.5, **kwargs: Tensor,

@@ -38,3 +38,8 @@ class StableDiffusion_1(LatentDiffusionModel):
     def set_unet_context(self, *, timestep: Tensor, clip_text_embedding: Tensor, **_: Tensor) -> None:
         self.unet.set_timestep(timestep=timestep)
         self.unet.set_clip_text_embedding(clip_text_embedding=clip_text_embedding)
+
+    def _sag_adapter_type(self) -> type:
+        from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1.self_attention_guidance import SD1SAGAdapter
+
+        return SD1SAGAdapter

@@ -69,6 +69,20 @@ class StableDiffusion_XL(LatentDiffusionModel):
         self.unet.set_pooled_text_embedding(pooled_text_embedding=pooled_text_embedding)
         self.unet.set_time_ids(time_ids=time_ids)
 
+    def _sag_adapter_type(self) -> type:
+        from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.self_attention_guidance import SDXLSAGAdapter
+
+        return SDXLSAGAdapter
+
+    def _unconditional_half(  # type: ignore[override]
+        self, *, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor, **_: Tensor
+    ) -> dict[str, Tensor]:
+        return {
+            "clip_text_embedding": clip_text_embedding.chunk(2)[0],
+            "pooled_text_embedding": pooled_text_embedding.chunk(2)[0],
+            "time_ids": time_ids.chunk(2)[0],
+        }
+
     def forward(  # type: ignore[override]
         self,
         x: Tensor,
