@@ -132,6 +132,15 @@ int rb200_group_norm(void* stream, int dtype, const void* x, void* y, int64_t B,
                      int64_t C, int G, float eps, const void* gamma, const void* beta, int silu,
                      void* ws, size_t ws_bytes);
 
+/* GroupNorm with FIXED statistics (tiled VAE inference): replaces FixedGroupNorm.compute_group_norm,
+ * foundationals/latent_diffusion/auto_encoder.py:209-251.  stats: fp32 [B, G, 2] = (mean, 1/sqrt(var + eps))
+ * per (sample, group).  frozen == 0: the statistics of x are computed, WRITTEN to stats and applied (the
+ * adapter's first pass, on the downscaled image); frozen != 0: stats are read as they are and no statistics
+ * pass runs (every later tile). */
+int rb200_group_norm_fixed(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t HW,
+                           int64_t C, int G, float eps, const void* gamma, const void* beta, int silu,
+                           void* ws, size_t ws_bytes, float* stats, int frozen);
+
 /* ---- LayerNorm ------------------------------------------------------------------------------
  * Replaces fluxion/layers/norm.py:14-49 (row LN over the last dim) and, applied to the NHWC
  * pixels of a map, fluxion/layers/norm.py:95-127 (LayerNorm2d). x, y: [rows, C] contiguous. */

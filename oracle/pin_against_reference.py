@@ -210,6 +210,47 @@ def pin_vae(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'vae.safetensors'}")
 
 
+def pin_vae_tiled(write: bool) -> None:
+    """Tiled VAE inference (auto_encoder.py:209-279, 411-621): a 224x160 image in 128x96 tiles blended over 32 pixels
+    (2 x 2 tiles), GroupNorm statistics frozen from the resized image; own generator and fixture file."""
+    _import_reference()
+    import numpy as np
+    from PIL import Image
+    from refiners.fluxion.utils import image_to_tensor
+    from refiners.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+    from safetensors.torch import save_file
+
+    from oracle import vae as ovae
+    from oracle.weights import keyed_state_dict
+
+    print("LatentDiffusionAutoencoder, tiled inference")
+    pixels = (np.random.default_rng(3).random((160, 224, 3)) * 255).astype(np.uint8)
+    image = Image.fromarray(pixels)
+    tile, blending = (128, 96), 32  # (width, height)
+    with torch.no_grad():
+        lda = LatentDiffusionAutoencoder()
+        sdict = keyed_state_dict({k: tuple(v.shape) for k, v in lda.state_dict().items()}, seed=5)
+        lda.load_state_dict(sdict)
+        with lda.tiled_inference(image, tile_size=tile, blending=blending):
+            latents = lda.tiled_image_to_latents(image)
+            decoded = lda._tiled_decode(latents, lda._tile_size, blending)
+        full, small = image_to_tensor(image), image_to_tensor(image.resize(tile))
+        ovae.frozen_stats = {}
+        try:
+            ovae.capture_statistics(sdict, full, small)
+            mine_lat = ovae.tiled(sdict, ovae.encode, 2 * full - 1, (20, 28), (96, 128), blending, 8, 1, 4)
+            mine_dec = ovae.tiled(sdict, ovae.decode, latents, (20, 28), (96, 128), blending, 1, 8, 3)
+        finally:
+            ovae.frozen_stats = None
+        _close("tiled encode", mine_lat, latents)
+        _close("tiled decode", mine_dec, decoded)
+    fx = {"tiled.pixels": torch.from_numpy(pixels), "tiled.small": (small * 255).round().to(torch.uint8), "tiled.latents": latents,
+          "tiled.decoded": decoded}
+    if write:
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "vae_tiled.safetensors"))
+        print(f"  wrote {GOLDEN / 'vae_tiled.safetensors'}")
+
+
 def pin_dinov2(write: bool) -> None:
     """DINOv2 ViT (dinov2/vit.py:289-413): the published small model at 224x224, and a tiny register + SwiGLU
     configuration on a non-square input that exercises the antialiased bicubic resize of the positions."""
@@ -610,7 +651,7 @@ def main(write: bool) -> None:
 if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
-        "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-dinov2": pin_dinov2,
+        "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-vae-tiled": pin_vae_tiled, "--only-dinov2": pin_dinov2,
         "--only-clip": pin_clip, "--only-sag": pin_sag,
         "--only-full-size": pin_full_size,
     }

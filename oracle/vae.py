@@ -25,8 +25,22 @@ def _conv(sd: SD, prefix: str, x: Tensor, stride: int = 1, padding: int = 0) -> 
     return ops.conv2d(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"), stride=stride, padding=padding)
 
 
+# Tiled inference (auto_encoder.py:209-251 FixedGroupNorm): when ``frozen_stats`` is a dict, every GroupNorm - keyed by
+# its state-dict prefix - normalises with the (mean, var) per (sample, group) of the FIRST tensor it saw.
+frozen_stats: dict | None = None
+
+
 def _gn(sd: SD, prefix: str, x: Tensor, eps: float) -> Tensor:
-    return ops.group_norm(x, 32, sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+    if frozen_stats is None:
+        return ops.group_norm(x, 32, sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+    B, C = x.shape[:2]
+    g = x.reshape(B, 32, -1)
+    if prefix not in frozen_stats:
+        frozen_stats[prefix] = (g.mean(dim=2, keepdim=True), g.var(dim=2, keepdim=True, correction=0))
+    mean, var = frozen_stats[prefix]
+    y = ((g - mean) / torch.sqrt(var + eps)).reshape(x.shape)
+    shape = (1, C) + (1,) * (x.ndim - 2)
+    return y * sd[prefix + ".weight"].reshape(shape) + sd[prefix + ".bias"].reshape(shape)
 
 
 def resnet(sd: SD, prefix: str, x: Tensor) -> Tensor:
@@ -89,3 +103,58 @@ def encode(sd: SD, image: Tensor) -> Tensor:
 
 def decode(sd: SD, latents: Tensor) -> Tensor:
     return decoder(sd, latents / ENCODER_SCALE)
+
+
+# ------------------------------------------------------------------------------------------ tiled inference
+def blending_mask(height: int, width: int, blending: int, edges: tuple[bool, bool, bool, bool]) -> Tensor:
+    """auto_encoder.py:254-279: linear ramps towards the borders that are not image borders (top, bottom, left, right)."""
+    mask = torch.ones(height, width)
+    if blending == 0:
+        return mask
+    n = min(blending, min(height, width) // 2)
+    ramp = torch.linspace(0, 1, n)
+    if not edges[0]:
+        mask[:n] *= ramp[:, None]
+    if not edges[1]:
+        mask[-n:] *= ramp.flip(0)[:, None]
+    if not edges[2]:
+        mask[:, :n] *= ramp[None, :]
+    if not edges[3]:
+        mask[:, -n:] *= ramp.flip(0)[None, :]
+    return mask
+
+
+def latent_tiles(height: int, width: int, tile_h: int, tile_w: int, overlap: int) -> list[tuple[int, int, int, int]]:
+    """auto_encoder.py:411-428: (top, left, bottom, right), columns outermost."""
+    return [
+        (y, x, min(height, y + tile_h), min(width, x + tile_w))
+        for x in range(0, max(width - overlap, 1), tile_w - overlap)
+        for y in range(0, max(height - overlap, 1), tile_h - overlap)
+    ]
+
+
+def capture_statistics(sd: SD, image01: Tensor, small01: Tensor) -> None:
+    """auto_encoder.py:430-456: the resized copy ``small01`` (values in [0, 1]) is clamped to the range of the full image,
+    moved to its per-channel mean / standard deviation, and run through encode + decode with ``frozen_stats`` empty."""
+    small = small01.clamp(min=image01.min(), max=image01.max())
+    std, mean = torch.std_mean(image01, dim=[0, 2, 3], keepdim=True)
+    small_std, small_mean = torch.std_mean(small, dim=[0, 2, 3], keepdim=True)
+    small = (small - small_mean) * (std / small_std) + mean
+    decode(sd, encode(sd, 2 * small - 1))
+
+
+def tiled(sd: SD, run, source: Tensor, latent_hw: tuple[int, int], tile_hw: tuple[int, int], blending: int, k_in: int, k_out: int,
+          channels: int) -> Tensor:
+    """auto_encoder.py:465-583 (encode: k_in 8, k_out 1; decode: k_in 1, k_out 8; ``tile_hw`` in pixels)."""
+    H, W = latent_hw
+    tiles = latent_tiles(H, W, tile_hw[0] // 8, tile_hw[1] // 8, blending // 8)
+    if len(tiles) == 1:
+        return run(sd, source)
+    out = torch.zeros(1, channels, H * k_out, W * k_out)
+    weight = torch.zeros_like(out)
+    for top, left, bottom, right in tiles:
+        piece = run(sd, source[:, :, top * k_in : bottom * k_in, left * k_in : right * k_in])
+        mask = blending_mask((bottom - top) * k_out, (right - left) * k_out, blending * k_out // 8, (top == 0, bottom == H, left == 0, right == W))
+        out[:, :, top * k_out : bottom * k_out, left * k_out : right * k_out] += piece * mask
+        weight[:, :, top * k_out : bottom * k_out, left * k_out : right * k_out] += mask
+    return out / weight

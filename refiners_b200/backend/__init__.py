@@ -86,6 +86,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_conv2d": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _L, _L, _L, _L, _L, _I, _I, _I, _I, _I]),
     "rb200_group_norm_workspace_bytes": (_Z, [_L, _L, _I]),
     "rb200_group_norm": (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _F, _P, _P, _I, _P, _Z]),
+    "rb200_group_norm_fixed": (_I, [_P, _I, _P, _P, _L, _L, _L, _I, _F, _P, _P, _I, _P, _Z, _P, _I]),
     "rb200_layer_norm": (_I, [_P, _I, _P, _P, _L, _L, _F, _P, _P]),
     "rb200_unary": (_I, [_P, _I, _P, _P, _L, _I]),
     "rb200_geglu": (_I, [_P, _I, _P, _P, _L, _L]),
@@ -1022,6 +1023,34 @@ def conv2d_module(x: Tensor, module: Any, **fused: Any) -> Tensor:
 def group_norm(x: Tensor, groups: int, gamma: Tensor, beta: Tensor, eps: float, silu: bool = False) -> Tensor:
     _inference_only(x, gamma, beta)
     return _ops.group_norm(x, groups, gamma, beta, eps, silu)
+
+
+def group_norm_fixed(
+    x: Tensor, groups: int, gamma: Tensor, beta: Tensor, eps: float, stats: Tensor | None = None
+) -> tuple[Tensor, Tensor]:
+    """GroupNorm of an NCHW map with statistics that are captured once and then frozen (tiled VAE inference; see
+    rb200_group_norm_fixed).  ``stats`` is None on the capturing pass; the fp32 ``[B, groups, 2]`` (mean, rstd) buffer
+    this returns is handed back on every later call."""
+    _inference_only(x, gamma, beta)
+    _same(x, gamma, beta)
+    if x.ndim != 4:
+        raise BackendError("group_norm_fixed expects [B, C, H, W]")
+    lib = load_library()
+    B, C, H, W = x.shape
+    frozen = stats is not None
+    if stats is None:
+        stats = torch.empty((B, groups, 2), device=x.device, dtype=torch.float32)
+    elif stats.shape != (B, groups, 2) or stats.dtype != torch.float32 or stats.device != x.device or not stats.is_contiguous():
+        raise BackendError(f"group_norm_fixed: statistics {tuple(stats.shape)} do not fit a batch of {B} with {groups} groups")
+    xc = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty_like(xc, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.rb200_group_norm_workspace_bytes(B, H * W, groups)
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        if xc.numel():
+            _check(lib.rb200_group_norm_fixed(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), B, H * W, C, groups, float(eps),
+                                              gamma.data_ptr(), beta.data_ptr(), 0, ws.data_ptr(), ws_bytes, stats.data_ptr(), int(frozen)))
+    return y, stats
 
 
 def layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float) -> Tensor:

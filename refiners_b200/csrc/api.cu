@@ -41,7 +41,7 @@ int sm_count() {
 }
 
 // implemented in norm_kernels.cu
-int group_norm_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int, float, const void*, const void*, int, void*, size_t);
+int group_norm_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int, float, const void*, const void*, int, void*, size_t, float*, int);
 size_t group_norm_ws(int64_t, int64_t, int);
 int layer_norm_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, float, const void*, const void*);
 int unary_impl(cudaStream_t, int, const void*, void*, int64_t, int);
@@ -188,7 +188,15 @@ int rb200_group_norm(void* stream, int dtype, const void* x, void* y, int64_t B,
                      const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes) {
   if (bad_dtype(dtype) || !x || !y || !gamma || !beta) RB200_FAIL(-1, "group_norm: bad arguments");
   if (B <= 0 || HW <= 0 || C <= 0) return 0;
-  return group_norm_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, HW, C, G, eps, gamma, beta, silu, ws, ws_bytes);
+  return group_norm_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, HW, C, G, eps, gamma, beta, silu, ws, ws_bytes, nullptr, 0);
+}
+
+int rb200_group_norm_fixed(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G, float eps,
+                           const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes, float* stats, int frozen) {
+  if (bad_dtype(dtype) || !x || !y || !gamma || !beta || !stats) RB200_FAIL(-1, "group_norm_fixed: bad arguments");
+  if (B <= 0 || HW <= 0 || C <= 0) return 0;
+  return group_norm_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, HW, C, G, eps, gamma, beta, silu, ws, ws_bytes, stats,
+                         frozen != 0);
 }
 
 int rb200_layer_norm(void* stream, int dtype, const void* x, void* y, int64_t rows, int64_t C, float eps, const void* gamma,

@@ -168,7 +168,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ x, T* __restrict__ y, cons
 
 template <typename T, int V>
 int gn_launch(cudaStream_t st, const T* x, T* y, int64_t B, int64_t HW, int C, int G, float eps, const T* gamma,
-              const T* beta, int silu, float* part) {
+              const T* beta, int silu, float* part, float* fixed_stats, int frozen) {
   const int CV = C / V;
   if (CV > 1024) RB200_FAIL(-1, "group_norm: C=%d too wide for this layout", C);
   const int pix = gn_pix(B, HW);
@@ -181,12 +181,16 @@ int gn_launch(cudaStream_t st, const T* x, T* y, int64_t B, int64_t HW, int C, i
   const size_t sm1 = size_t(lanes) * C * 2 * sizeof(float);
   if (sm1 > 200 * 1024) RB200_FAIL(-1, "group_norm: shared memory need %zu too large", sm1);
   if (sm1 > 48 * 1024) cudaFuncSetAttribute(gn_partial_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm1));
-  float* stats = part + size_t(B) * chunks * G * 2;
-  gn_partial_kernel<T, V><<<grid, block, sm1, st>>>(x, part, HW, C, G, chunks, pix);
-  RB200_CHECK_LAUNCH("gn_partial");
-  const int total = int(B) * G;
-  gn_finalize_kernel<<<unsigned(ceil_div(int64_t(total) * 32, 256)), 256, 0, st>>>(part, stats, HW, C, G, chunks, eps, total);
-  RB200_CHECK_LAUNCH("gn_finalize");
+  // (mean, rstd) per (sample, group): the workspace's own slot, or the caller's buffer - which is either filled here
+  // (first pass of a FixedGroupNorm) or, when `frozen`, read as it is: no statistics pass at all
+  float* stats = fixed_stats ? fixed_stats : part + size_t(B) * chunks * G * 2;
+  if (!frozen) {
+    gn_partial_kernel<T, V><<<grid, block, sm1, st>>>(x, part, HW, C, G, chunks, pix);
+    RB200_CHECK_LAUNCH("gn_partial");
+    const int total = int(B) * G;
+    gn_finalize_kernel<<<unsigned(ceil_div(int64_t(total) * 32, 256)), 256, 0, st>>>(part, stats, HW, C, G, chunks, eps, total);
+    RB200_CHECK_LAUNCH("gn_finalize");
+  }
   gn_apply_kernel<T, V><<<grid, block, 2 * G * sizeof(float), st>>>(x, y, stats, gamma, beta, HW, C, G, pix, silu);
   RB200_CHECK_LAUNCH("gn_apply");
   return 0;
@@ -194,12 +198,12 @@ int gn_launch(cudaStream_t st, const T* x, T* y, int64_t B, int64_t HW, int C, i
 
 template <typename T>
 int gn_dispatch(cudaStream_t st, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G, float eps,
-                const void* gamma, const void* beta, int silu, float* part) {
+                const void* gamma, const void* beta, int silu, float* part, float* fixed_stats, int frozen) {
   constexpr int VMAX = 16 / sizeof(T);
   const bool aligned = (C % VMAX == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
   if (aligned)
-    return gn_launch<T, VMAX>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part);
-  return gn_launch<T, 1>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part);
+    return gn_launch<T, VMAX>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part, fixed_stats, frozen);
+  return gn_launch<T, 1>(st, (const T*)x, (T*)y, B, HW, int(C), G, eps, (const T*)gamma, (const T*)beta, silu, part, fixed_stats, frozen);
 }
 
 // ------------------------------------------------------------------------------ LayerNorm
@@ -628,12 +632,13 @@ inline bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 1
 size_t group_norm_ws(int64_t B, int64_t HW, int G);
 
 int group_norm_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int64_t HW, int64_t C, int G,
-                    float eps, const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes) {
+                    float eps, const void* gamma, const void* beta, int silu, void* ws, size_t ws_bytes, float* fixed_stats,
+                    int frozen) {
   if (G <= 0 || C % G != 0) RB200_FAIL(-1, "group_norm: C=%lld not divisible by G=%d", (long long)C, G);
   const size_t need = group_norm_ws(B, HW, G);
   if (ws_bytes < need || ws == nullptr) RB200_FAIL(-1, "group_norm: workspace %zu < %zu", ws_bytes, need);
   if (B > 65535) RB200_FAIL(-1, "group_norm: batch %lld too large", (long long)B);
-  DISPATCH_T(dtype, return gn_dispatch<T>(st, x, y, B, HW, C, G, eps, gamma, beta, silu, static_cast<float*>(ws)));
+  DISPATCH_T(dtype, return gn_dispatch<T>(st, x, y, B, HW, C, G, eps, gamma, beta, silu, static_cast<float*>(ws), fixed_stats, frozen));
   return 0;
 }
 

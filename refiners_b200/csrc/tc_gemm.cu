@@ -517,143 +517,129 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         m_lin = int64_t(mt) * BM + row;
         valid = m_lin < p.M;
       }
-      // The residual rows of the first column chunk are fetched BEFORE waiting for the accumulator, while the tensor
-      // core is still working on it; every later chunk's rows are requested one chunk ahead, together with its TMEM
-      // load, so the epilogue never sits on a dependent global-load latency (two 16-register buffers, not MAXC).
+      // The residual rows of this tile are fetched BEFORE waiting for the accumulator, while the tensor core is
+      // still working on it: the epilogue then never sits on a dependent global-load latency per column chunk.
       constexpr int MAXC = (BN / 32 + 1) / 2;
-      uint4 rpre[2][4];
+      uint4 rpre[MAXC][4];
       const bool rfast = res != nullptr && !geglu && valid && (int64_t(nt) * BN + BN <= p.N) &&
                          ((reinterpret_cast<uintptr_t>(res + m_lin * p.ldr + int64_t(nt) * BN) & 15) == 0);
-      const uint4* rs4 = reinterpret_cast<const uint4*>(res + m_lin * p.ldr + int64_t(nt) * BN);
       if (rfast) {
+        const uint4* rs = reinterpret_cast<const uint4*>(res + m_lin * p.ldr + int64_t(nt) * BN);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rpre[0][q] = __ldg(rs4 + half * 4 + q);
+        for (int cc = 0; cc < MAXC; ++cc) {
+          const int c = half + 2 * cc;
+          if (c < BN / 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rpre[cc][q] = __ldg(rs + c * 4 + q);
+          }
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + uint32_t(acc * BN) + (uint32_t(lg * 32) << 16);
-      // Two register buffers: the TMEM load of the next 32-column chunk is in flight while this chunk is converted and
-      // stored (a tcgen05.ld + wait::ld costs ~140 cycles before the first value can be used - measured with
-      // tools/probes/tmem_probe.cu - and four chunks per tile per warp pace the kernel on short-K shapes such as the
-      // 640-wide transformer blocks, whose main loop lasts only ~5000 cycles per tile).
-      uint32_t raw2[2][32];
-      auto chunk_live = [&](int cc) {  // warp-uniform: does chunk cc of this warp exist inside the matrix?
-        const int c = half + 2 * cc;
-        return cc < MAXC && c < BN / 32 && int64_t(nt) * BN + c * 32 < p.N;
-      };
-      if (chunk_live(0)) {
-        tmem_ld_32x32(taddr + uint32_t(half * 32), raw2[0]);
-        tmem_ld_wait();
-      }
 #pragma unroll
       for (int cc = 0; cc < MAXC; ++cc) {
-        if (!chunk_live(cc)) break;
         const int c = half + 2 * cc;
+        if (c >= BN / 32) break;
         const int64_t n0 = int64_t(nt) * BN + c * 32;
-        if (chunk_live(cc + 1)) {
-          tmem_ld_32x32(taddr + uint32_t((c + 2) * 32), raw2[(cc + 1) & 1]);
-          if (rfast) {
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld_32x32(taddr + uint32_t(c * 32), raw);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float v[32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rpre[(cc + 1) & 1][q] = __ldg(rs4 + (c + 2) * 4 + q);
-          }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        const bool full = (n0 + 32 <= p.N);
+        if (p.colscale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < p.N) v[j] *= __ldg(p.colscale + n0 + j);
         }
-        const uint32_t(&raw)[32] = raw2[cc & 1];
-        if (valid) {
-          float v[32];
+        if (bias) {
+          if (full && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          const bool full = (n0 + 32 <= p.N);
-          if (p.colscale) {
+            for (int j = 0; j < 32; j += 8) add8<T>(v + j, bias + n0 + j);
+          } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (full || n0 + j < p.N) v[j] *= __ldg(p.colscale + n0 + j);
-          }
-          if (bias) {
-            if (full && ((reinterpret_cast<uintptr_t>(bias + n0) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) add8<T>(v + j, bias + n0 + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += to_f(bias[n0 + j]);
-            }
-          }
-          if (cbias) {
-            const T* cb = cbias + b_idx * p.N + n0;
-            if (full && ((reinterpret_cast<uintptr_t>(cb) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) add8<T>(v + j, cb + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) v[j] += to_f(cb[j]);
-            }
-          }
-          if (geglu) {
-            // packed columns: [16 values | 16 gates]; output column block n0 / 2
-            const int64_t no = n0 >> 1;
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_fast(v[16 + j]);
-            T* dst = y + m_lin * p.ldy + no;
-            if (res) {
-              const T* rs = res + m_lin * p.ldr + no;
-              if ((reinterpret_cast<uintptr_t>(rs) & 15) == 0) {
-                add8<T>(o, rs);
-                add8<T>(o + 8, rs + 8);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] += to_f(rs[j]);
-              }
-            }
-            if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-              uint4 u0, u1;
-              u0.x = pack2<T>(o[0], o[1]);  u0.y = pack2<T>(o[2], o[3]);  u0.z = pack2<T>(o[4], o[5]);   u0.w = pack2<T>(o[6], o[7]);
-              u1.x = pack2<T>(o[8], o[9]);  u1.y = pack2<T>(o[10], o[11]); u1.z = pack2<T>(o[12], o[13]); u1.w = pack2<T>(o[14], o[15]);
-              reinterpret_cast<uint4*>(dst)[0] = u0;
-              reinterpret_cast<uint4*>(dst)[1] = u1;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) dst[j] = from_f<T>(o[j]);
-            }
-          } else {
-            if (p.epilogue != RB200_EPI_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_epilogue_fast(v[j], p.epilogue);
-            }
-            T* dst = y + m_lin * p.ldy + n0;
-            if (rfast) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) add8v<T>(v + 8 * q, rpre[cc & 1][q]);
-            } else if (res) {
-              const T* rs = res + m_lin * p.ldr + n0;
-              if (full && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) add8<T>(v + j, rs + j);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < p.N) v[j] += to_f(rs[j]);
-              }
-            }
-            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 u;
-                u.x = pack2<T>(v[j], v[j + 1]);
-                u.y = pack2<T>(v[j + 2], v[j + 3]);
-                u.z = pack2<T>(v[j + 4], v[j + 5]);
-                u.w = pack2<T>(v[j + 6], v[j + 7]);
-                *reinterpret_cast<uint4*>(dst + j) = u;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < p.N) dst[j] = from_f<T>(v[j]);
-            }
+              if (n0 + j < p.N) v[j] += to_f(bias[n0 + j]);
           }
         }
-        tmem_ld_wait();  // the next chunk (if any) has landed
+        if (cbias) {
+          const T* cb = cbias + b_idx * p.N + n0;
+          if (full && ((reinterpret_cast<uintptr_t>(cb) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) add8<T>(v + j, cb + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += to_f(cb[j]);
+          }
+        }
+        if (geglu) {
+          // packed columns: [16 values | 16 gates]; output column block n0 / 2
+          const int64_t no = n0 >> 1;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf_fast(v[16 + j]);
+          T* dst = y + m_lin * p.ldy + no;
+          if (res) {
+            const T* rs = res + m_lin * p.ldr + no;
+            if ((reinterpret_cast<uintptr_t>(rs) & 15) == 0) {
+              add8<T>(o, rs);
+              add8<T>(o + 8, rs + 8);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] += to_f(rs[j]);
+            }
+          }
+          if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            uint4 u0, u1;
+            u0.x = pack2<T>(o[0], o[1]);  u0.y = pack2<T>(o[2], o[3]);  u0.z = pack2<T>(o[4], o[5]);   u0.w = pack2<T>(o[6], o[7]);
+            u1.x = pack2<T>(o[8], o[9]);  u1.y = pack2<T>(o[10], o[11]); u1.z = pack2<T>(o[12], o[13]); u1.w = pack2<T>(o[14], o[15]);
+            reinterpret_cast<uint4*>(dst)[0] = u0;
+            reinterpret_cast<uint4*>(dst)[1] = u1;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = from_f<T>(o[j]);
+          }
+          continue;
+        }
+        if (p.epilogue != RB200_EPI_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_epilogue_fast(v[j], p.epilogue);
+        }
+        T* dst = y + m_lin * p.ldy + n0;
+        if (rfast) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) add8v<T>(v + 8 * q, rpre[cc][q]);
+        } else if (res) {
+          const T* rs = res + m_lin * p.ldr + n0;
+          if (full && ((reinterpret_cast<uintptr_t>(rs) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) add8<T>(v + j, rs + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) v[j] += to_f(rs[j]);
+          }
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            u.x = pack2<T>(v[j], v[j + 1]);
+            u.y = pack2<T>(v[j + 2], v[j + 3]);
+            u.z = pack2<T>(v[j + 4], v[j + 5]);
+            u.w = pack2<T>(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(dst + j) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) dst[j] = from_f<T>(v[j]);
+        }
       }
       // all TMEM reads of this warp are complete (wait::ld above): release the accumulator
       tcgen05_fence_before();

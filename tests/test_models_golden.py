@@ -218,6 +218,52 @@ def test_vae_host():
     assert (image_to_tensor(images[0]) - want).abs().max().item() <= 1 / 255 + 1e-6
 
 
+def tiled_vae(device, dtype):
+    """The reference's recorded tiled round trip (224x160 image, 128x96 tiles, 32-pixel blend): (latents, decoded,
+    tree restored)."""
+    from PIL import Image
+
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import FixedGroupNorm, LatentDiffusionAutoencoder
+
+    f = load_file(str(GOLDEN / "vae_tiled.safetensors"))
+    lda = LatentDiffusionAutoencoder(device="meta")
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in lda.state_dict().items()}, seed=5)
+    lda.load_state_dict({k: v.to(device, dtype) for k, v in sd.items()}, assign=True)
+    image = Image.fromarray(f["tiled.pixels"].numpy())
+    before = repr(lda)
+    with pytest.raises(ValueError):
+        lda.tiled_image_to_latents(image)
+    with no_grad(), lda.tiled_inference(image, tile_size=(128, 96), blending=32):
+        assert len([*lda.layers(FixedGroupNorm)]) == 52 and all(n.mean is not None for n in lda.layers(FixedGroupNorm))
+        latents = lda.tiled_image_to_latents(image)
+        decoded = lda._tiled_decode(f["tiled.latents"].to(device, dtype), lda._tile_size, 32)
+        picture = lda.tiled_latents_to_image(f["tiled.latents"].to(device, dtype))
+    assert picture.size == (224, 160) and repr(lda) == before
+    return f, latents, decoded
+
+
+def test_vae_tiled_host():
+    """Tiled inference with frozen GroupNorm statistics against the reference's recorded latents and pixels, and the
+    oracle's restatement against the same."""
+    from oracle import vae as ovae
+
+    f, latents, decoded = tiled_vae("cpu", torch.float32)
+    check(latents, f["tiled.latents"], "host")
+    check(decoded, f["tiled.decoded"], "host")
+    from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
+
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in LatentDiffusionAutoencoder(device="meta").state_dict().items()}, seed=5)
+    full = f["tiled.pixels"].permute(2, 0, 1)[None].float() / 255
+    small = f["tiled.small"].float() / 255
+    ovae.frozen_stats = {}
+    try:
+        with no_grad():
+            ovae.capture_statistics(sd, full, small)
+            check(ovae.tiled(sd, ovae.decode, f["tiled.latents"], (20, 28), (96, 128), 32, 1, 8, 3), f["tiled.decoded"], "host")
+    finally:
+        ovae.frozen_stats = None
+
+
 def test_dinov2_host():
     """DINOv2 ViT on keyed weights against the reference: the published small model and a tiny
     registers + SwiGLU configuration whose input grid (6 x 5) differs from the positional grid (4 x 4)."""
@@ -289,6 +335,42 @@ def test_vae_gpu(cuda_device, dtype):
     with no_grad():
         check(lda.decode(f["vae.z"].to(cuda_device, dtype)), f["vae.decoded"], dtype)
         check(lda.encode(f["vae.image"].to(cuda_device, dtype)), f["vae.encoded"], dtype)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_vae_tiled_gpu(cuda_device, dtype):
+    """Same round trip with every tile on the kernels: GroupNorms run rb200_group_norm_fixed (statistics captured on the
+    resized image, frozen for the tiles)."""
+    f, latents, decoded = tiled_vae(cuda_device, dtype)
+    check(latents, f["tiled.latents"], dtype)
+    check(decoded, f["tiled.decoded"], dtype)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=str)
+def test_group_norm_fixed_kernel(cuda_device, dtype):
+    """rb200_group_norm_fixed: the capturing pass equals GroupNorm and returns (mean, rstd); a frozen pass applies those
+    statistics to a different tensor (checked against the formula in fp32)."""
+    from refiners_b200 import backend as B
+
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(2, 64, 9, 7, generator=gen) * 2 + 0.5).to(cuda_device, dtype)
+    other = torch.randn(2, 64, 5, 11, generator=gen).to(cuda_device, dtype)
+    gamma, beta = torch.randn(64, generator=gen).to(cuda_device, dtype), torch.randn(64, generator=gen).to(cuda_device, dtype)
+    y, stats = B.group_norm_fixed(x, 8, gamma, beta, 1e-5)
+    assert torch.equal(y, B.group_norm(x, 8, gamma, beta, 1e-5))
+    g = x.float().reshape(2, 8, -1)
+    assert torch.allclose(stats[..., 0], g.mean(2), atol=1e-5) and torch.allclose(stats[..., 1], (g.var(2, correction=0) + 1e-5).rsqrt(), rtol=1e-4)
+    kept = stats.clone()
+    z, again = B.group_norm_fixed(other, 8, gamma, beta, 1e-5, stats)
+    assert again is stats and torch.equal(stats, kept)
+    o = other.float().reshape(2, 8, -1)
+    want = ((o - stats[..., :1]) * stats[..., 1:]).reshape(other.shape) * gamma.float().view(1, -1, 1, 1) + beta.float().view(1, -1, 1, 1)
+    tol = {torch.float32: 1e-5, torch.bfloat16: 2**-7, torch.float16: 2**-10}[dtype]
+    assert (z.float() - want).abs().max().item() <= tol * want.abs().max().item()
+    with pytest.raises(B.BackendError):
+        B.group_norm_fixed(other[:1], 8, gamma, beta, 1e-5, stats)
 
 
 @pytest.mark.gpu
