@@ -78,7 +78,7 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename T, bool POLY>
+template <typename T, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const Attn2Params p) {
@@ -328,8 +328,9 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             const int i = c * 8 + q * 4;
             const float x0 = fmaf(s[i], p.scale_log2e, -mb), x1 = fmaf(s[i + 1], p.scale_log2e, -mb);
             const float x2 = fmaf(s[i + 2], p.scale_log2e, -mb), x3 = fmaf(s[i + 3], p.scale_log2e, -mb);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2);
-            const float p3 = POLY ? ex2_poly(x3) : ex2_approx(x3);
+            const float p0 = ex2_approx(x0), p2 = ex2_approx(x2);
+            const float p1 = POLY >= 2 ? ex2_poly(x1) : ex2_approx(x1);
+            const float p3 = POLY >= 1 ? ex2_poly(x3) : ex2_approx(x3);
             psum0 += p0 + p1;
             psum1 += p2 + p3;
             pk[q * 2] = pack2<T>(p0, p1);
@@ -428,7 +429,7 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, bool POLY>
+template <typename T, int POLY>
 int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const Attn2Params& prm) {
   static PerDeviceOnce configured;
   if (configured.needed()) {
@@ -451,7 +452,7 @@ int env_int(const char* name, int fallback) {
 }  // namespace
 
 // RB200_ATTN_V2: 0 = always the first-generation kernel, 1 (default) = this kernel where it applies.
-// RB200_ATTN_POLY: 1 = every fourth exponential on the FMA pipe, 0 (default) = all on MUFU (measured: no gain with two
+// RB200_ATTN_POLY: 1 / 2 = every fourth / every second exponential on the FMA pipe, 0 (default) = all on MUFU (measured: no gain with two
 // softmax warps per scheduler).
 bool tc_sdpa2_supported(const SdpaProblem& p) {
   static const int enabled = env_int("RB200_ATTN_V2", 1);
@@ -488,8 +489,9 @@ int tc_sdpa2(cudaStream_t st, const SdpaProblem& p) {
   prm.d_out = p.D;
   static const int poly = env_int("RB200_ATTN_POLY", 0);
   const bool bf = p.dtype == RB200_BF16;
-  if (poly) return bf ? launch<__nv_bfloat16, true>(st, mq, mk, mv, prm) : launch<__half, true>(st, mq, mk, mv, prm);
-  return bf ? launch<__nv_bfloat16, false>(st, mq, mk, mv, prm) : launch<__half, false>(st, mq, mk, mv, prm);
+  if (poly >= 2) return bf ? launch<__nv_bfloat16, 2>(st, mq, mk, mv, prm) : launch<__half, 2>(st, mq, mk, mv, prm);
+  if (poly == 1) return bf ? launch<__nv_bfloat16, 1>(st, mq, mk, mv, prm) : launch<__half, 1>(st, mq, mk, mv, prm);
+  return bf ? launch<__nv_bfloat16, 0>(st, mq, mk, mv, prm) : launch<__half, 0>(st, mq, mk, mv, prm);
 }
 
 }  // namespace rb200

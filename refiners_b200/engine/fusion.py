@@ -201,6 +201,10 @@ def forward_with_residual(chain: Any, args: tuple[Any, ...], residual: Tensor) -
     chain._reset_context()
     if isinstance(out, Tensor) and out.is_cuda and out.shape == residual.shape and out.dtype == residual.dtype:
         return B.add(out, residual)
+    if isinstance(out, (int, float)) and out == 0:
+        # ResidualAccumulator on a slot that still holds its initial 0.0 (unet.py:54-63 of the reference): x + 0.0 is x;
+        # no kernel of this library writes in place, so handing the same tensor on is safe (10 full-size ATen adds per step)
+        return residual
     return out + residual
 
 
