@@ -324,6 +324,48 @@ def pin_clip(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'clip.safetensors'}")
 
 
+PROMPTS = ["a photo of a cat", "", "An astronaut riding a horse on Mars, 4k, highly-detailed!!"]
+
+
+def pin_clip_text(write: bool) -> None:
+    """CLIP text towers: CLIPTextEncoderL (SD 1.5's prompt encoder) and SDXL's DoubleTextEncoder (L + bigG + pooling) on three
+    prompts, keyed weights; the token ids are stored too, so the GPU box needs no vocabulary file.  Own fixture file."""
+    _import_reference()
+    from refiners.foundationals.clip.text_encoder import CLIPTextEncoderL
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.text_encoder import DoubleTextEncoder
+    from safetensors.torch import save_file
+
+    from oracle import clip as oclip
+    from oracle.weights import keyed_state_dict
+
+    print("CLIP text encoders")
+    fx = {}
+    with torch.no_grad():
+        tower = CLIPTextEncoderL()
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in tower.state_dict().items()}, seed=21)
+        tower.load_state_dict(sd)
+        tokens = tower[0](PROMPTS)
+        y = tower(PROMPTS)
+        _close("CLIPTextEncoderL", oclip.text_encoder(sd, tokens, num_layers=12, heads=12, quick_gelu=True), y)
+        fx.update({"l.tokens": tokens, "l.y": y})
+        del tower
+        double = DoubleTextEncoder()
+        sd = keyed_state_dict({k: tuple(v.shape) for k, v in double.state_dict().items()}, seed=22)
+        double.load_state_dict(sd)
+        from refiners.foundationals.clip.tokenizer import CLIPTokenizer
+
+        tokens_g = CLIPTokenizer(pad_token_id=0)(PROMPTS)
+        embedding, pooled = double(PROMPTS)
+        towers = oclip.split_double_text_encoder(sd)
+        mine = oclip.double_text_encoder(*towers, tokens, tokens_g)
+        _close("DoubleTextEncoder embedding", mine[0], embedding)
+        _close("DoubleTextEncoder pooled", mine[1], pooled)
+        fx.update({"xl.tokens_g": tokens_g, "xl.embedding": embedding, "xl.pooled": pooled})
+    if write:
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "clip_text.safetensors"))
+        print(f"  wrote {GOLDEN / 'clip_text.safetensors'}")
+
+
 def pin_full_size(write: bool) -> None:
     """BASELINE-size cases (oracle/cases.py): SDXLUNet at 128x128 latents plain (config 2), with 700 LoRA
     adapters + IP-Adapter (config 3), with ControlLora (config 4), one full StableDiffusion_XL step with CFG +
@@ -652,7 +694,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-vae-tiled": pin_vae_tiled, "--only-dinov2": pin_dinov2,
-        "--only-clip": pin_clip, "--only-sag": pin_sag,
+        "--only-clip": pin_clip, "--only-clip-text": pin_clip_text, "--only-sag": pin_sag,
         "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]

@@ -66,6 +66,8 @@ struct Attn2Params {
   float scale_log2e;
   uint32_t idesc_qk, idesc_pv;
   int d_out;
+  int stagger;          // experiment (RB200_ATTN_STAGGER): 1 = tile B's first exponential phase of a work item waits for tile A's,
+                        // 2 = the two tiles' exponential phases alternate strictly (turnstile on named barriers 3 / 4)
 };
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -320,6 +322,12 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // instead of 32)
         if (j > 0 && !waited_o) mbar_wait(&bar_o[g], (t - 1) & 1, 11);
         if (j == 0 && t > 0) mbar_wait(&bar_o[g], (t - 1) & 1, 12);  // ... of the previous work item's last tile
+        if (p.stagger == 1) {
+          if (g == 1 && j == 0) named_bar_sync(3, 512);
+        } else if (p.stagger == 2) {
+          if (g == 1) named_bar_sync(3, 512);
+          else if (t > 0) named_bar_sync(4, 512);
+        }
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           uint32_t pk[4];
@@ -339,6 +347,11 @@ tc_sdpa2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           st_shared_v4(prow + ((c ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
         }
         l_run += psum0 + psum1;
+        if (p.stagger == 1) {
+          if (g == 0 && j == 0) named_bar_arrive(3, 512);
+        } else if (p.stagger == 2) {
+          named_bar_arrive(g == 0 ? 3 : 4, 512);
+        }
         fence_proxy_async();      // generic-proxy writes -> visible to the tensor core (async proxy)
         tcgen05_fence_before();   // also orders a rescale's tcgen05.st before the MMA that the arrive releases
         __syncwarp();
@@ -487,6 +500,8 @@ int tc_sdpa2(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_qk = common | (uint32_t(KT >> 3) << 17);                // D = 128 x 128, A and B K-major
   prm.idesc_pv = common | (uint32_t(HD >> 3) << 17) | (1u << 16);   // D = 128 x 64, B (= V) MN-major
   prm.d_out = p.D;
+  static const int stagger = env_int("RB200_ATTN_STAGGER", 0);
+  prm.stagger = stagger;
   static const int poly = env_int("RB200_ATTN_POLY", 0);
   const bool bf = p.dtype == RB200_BF16;
   if (poly >= 2) return bf ? launch<__nv_bfloat16, 2>(st, mq, mk, mv, prm) : launch<__half, 2>(st, mq, mk, mv, prm);

@@ -171,6 +171,23 @@ class LatentDiffusionModel(fl.Module, ABC):
                 )
         return self.solver(latents, predicted_noise=prediction, step=step)
 
+    # -- prompts ------------------------------------------------------------------------------------------
+    def compute_clip_text_embedding(self, text: str | list[str], negative_text: str | list[str] = "") -> Any:
+        """What ``clip_text_encoder`` makes of the prompt(s); with classifier-free guidance the negative prompt's result
+        comes first in the batch (unconditional | conditional).  A tower that returns several tensors (SDXL: token and
+        pooled embeddings) has each of them batched that way.  Reference: stable_diffusion_1/model.py:114-133,
+        stable_diffusion_xl/model.py:87-111."""
+        assert self.clip_text_encoder is not None, "this model was built without a text encoder"
+        prompts = [text] if isinstance(text, str) else text
+        if not self.classifier_free_guidance:
+            return self.clip_text_encoder(prompts)
+        negatives = [negative_text] if isinstance(negative_text, str) else negative_text
+        assert len(prompts) == len(negatives), "The length of the text list and negative_text should be the same"
+        wanted, unwanted = self.clip_text_encoder(prompts), self.clip_text_encoder(negatives)
+        if isinstance(wanted, tuple):
+            return tuple(torch.cat((no, yes), dim=0) for no, yes in zip(unwanted, wanted))
+        return torch.cat((unwanted, wanted))
+
     # -- bookkeeping around the loop ------------------------------------------------------------------------
     @property
     def steps(self) -> list[int]:

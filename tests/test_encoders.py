@@ -109,3 +109,127 @@ def test_vision_tower_gpu(cuda_device, case, dtype):
     t_max, t_rms = rel_err(eager, want)
     print(f"\n[{case} bf16] engine max-abs {e_max:.3e} rms {e_rms:.3e} | torch-eager bf16 max-abs {t_max:.3e} rms {t_rms:.3e} (relative to max|ref|)")
     assert e_rms <= t_rms + 1e-3 and e_max <= 1.25 * t_max + 1e-3
+
+
+# ------------------------------------------------------------------------------------------ CLIP text towers
+REF = Path("/root/reference/src/refiners")
+PROMPTS = ["a photo of a cat", "", "An astronaut riding a horse on Mars, 4k, highly-detailed!!"]
+
+
+def text_tower(device="cpu", dtype=torch.float32):
+    from refiners_b200.foundationals.clip import CLIPTextEncoderL
+
+    return keyed(CLIPTextEncoderL(device="meta"), 21, device, dtype)
+
+
+def double_tower(device, dtype):
+    from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.text_encoder import DoubleTextEncoder
+
+    return keyed(DoubleTextEncoder(device="meta"), 22, device, dtype)
+
+
+def test_clip_text_encoder_host():
+    """CLIPTextEncoderL on recorded token ids (no vocabulary file needed) against the reference's output; the oracle too."""
+    f = load_file(str(GOLDEN / "clip_text.safetensors"))
+    tower = text_tower()
+    with no_grad():
+        e_max, _ = rel_err(tower(f["l.tokens"]), f["l.y"])
+        o_max, _ = rel_err(oclip.text_encoder(dict(tower.state_dict()), f["l.tokens"], num_layers=12, heads=12, quick_gelu=True), f["l.y"])
+    assert e_max <= 1e-5 and o_max <= 1e-5, (e_max, o_max)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="/root/reference is not mounted here (the BPE merge table ships with it)")
+def test_clip_tokenizer_against_the_reference():
+    from oracle.pin_against_reference import _import_reference
+
+    _import_reference()
+    from refiners.foundationals.clip.tokenizer import CLIPTokenizer as Theirs
+
+    from refiners_b200.foundationals.clip import CLIPTokenizer
+    from tests.test_reference_structure import same
+
+    vocabulary = REF / "foundationals/clip/bpe_simple_vocab_16e6.txt.gz"
+    mine, theirs = CLIPTokenizer(vocabulary_path=vocabulary), Theirs()
+    f = load_file(str(GOLDEN / "clip_text.safetensors"))
+    assert torch.equal(mine(PROMPTS), f["l.tokens"]) and torch.equal(CLIPTokenizer(vocabulary_path=vocabulary, pad_token_id=0)(PROMPTS), f["xl.tokens_g"])
+    texts = [*PROMPTS, "naïve café — ünïcödé ☃ test_123 it's they're", "banana bandana " * 30, "<|startoftext|>hello<|endoftext|> world",
+             "\t tabs\nand  newlines \x7f\x80"]
+    for text in texts:
+        assert torch.equal(mine(text), theirs(text)), text
+    assert torch.equal(mine(texts[:4]), theirs(texts[:4])) and torch.equal(mine.encode("hello world"), theirs.encode("hello world"))
+    assert mine.token_to_id_mapping == theirs.token_to_id_mapping
+    # trees and state-dict contract of the towers and of SDXL's double encoder (pooling adapter injected)
+    from refiners.foundationals.clip.text_encoder import CLIPTextEncoderG as RG, CLIPTextEncoderH as RH, CLIPTextEncoderL as RL
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.text_encoder import DoubleTextEncoder as RD
+
+    from refiners_b200.foundationals.clip import CLIPTextEncoderG, CLIPTextEncoderH, CLIPTextEncoderL
+    from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.text_encoder import DoubleTextEncoder
+
+    for ours, ref in ((CLIPTextEncoderL, RL), (CLIPTextEncoderH, RH), (CLIPTextEncoderG, RG), (DoubleTextEncoder, RD)):
+        same(ours(device="meta"), ref(device="meta"))
+    twin = DoubleTextEncoder(device="meta").structural_copy()
+    same(twin, RD(device="meta"))
+
+
+def test_prompt_embedding_api():
+    """LatentDiffusionModel.compute_clip_text_embedding: (negative | positive) batching, for one tensor and for a tuple."""
+    from refiners_b200.foundationals.latent_diffusion import StableDiffusion_1
+
+    class Fake(fl.Module):
+        def forward(self, text):
+            base = torch.tensor([[float(len(t))] for t in text])
+            return base, base + 0.5
+
+    sd = StableDiffusion_1(unet=fl.Chain(fl.Identity()), clip_text_encoder=None)
+    sd.clip_text_encoder = Fake()
+    tokens, pooled = sd.compute_clip_text_embedding(["ab", "abcd"], ["x", ""])
+    assert tokens.flatten().tolist() == [1.0, 0.0, 2.0, 4.0] and pooled.flatten().tolist() == [1.5, 0.5, 2.5, 4.5]
+    sd.classifier_free_guidance = False
+    assert sd.compute_clip_text_embedding("abc")[0].flatten().tolist() == [3.0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_clip_text_encoder_gpu(cuda_device, dtype):
+    """CLIPTextEncoderL on the kernels (causal attention on the CUDA-core flash kernel, quick GeLU, LayerNorm, GEMMs)."""
+    f = load_file(str(GOLDEN / "clip_text.safetensors"))
+    tower = text_tower(cuda_device, dtype)
+    with no_grad():
+        y = tower(f["l.tokens"])
+    e_max, e_rms = rel_err(y, f["l.y"])
+    if dtype == torch.float32:
+        assert e_max <= 2e-4, e_max
+        return
+    prev, oops.FAST = oops.FAST, True
+    try:
+        with torch.no_grad():
+            eager = oclip.text_encoder(dict(tower.state_dict()), f["l.tokens"].to(cuda_device), num_layers=12, heads=12, quick_gelu=True)
+    finally:
+        oops.FAST = prev
+    t_max, t_rms = rel_err(eager, f["l.y"])
+    print(f"\n[CLIPTextEncoderL bf16] engine max-abs {e_max:.3e} rms {e_rms:.3e} | torch-eager bf16 max-abs {t_max:.3e} rms {t_rms:.3e}")
+    assert e_rms <= t_rms + 1e-3 and e_max <= 1.25 * t_max + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_sdxl_double_text_encoder_gpu(cuda_device, dtype):
+    """SDXL's DoubleTextEncoder (L + bigG towers at their penultimate layer, pooled + projected bigG embedding) on recorded
+    token ids: the L tower's ids go in, the bigG tokenizer differs only in its padding id, so its ids are substituted."""
+    f = load_file(str(GOLDEN / "clip_text.safetensors"))
+    double = double_tower(cuda_device, dtype)
+    from refiners_b200.foundationals.clip import CLIPTextEncoderG, CLIPTokenizer
+
+    g_tokenizer = double.ensure_find(CLIPTextEncoderG).ensure_find(CLIPTokenizer) if double.find(CLIPTextEncoderG) else None
+    assert g_tokenizer is not None and g_tokenizer.pad_token_id == 0
+    pooling = double.layer(("Parallel", "TextEncoderWithPooling"), fl.Chain)
+    l_branch = double.layer(("Parallel", "CLIPTextEncoderL"), fl.Chain)
+    with no_grad():
+        hidden_l = l_branch(f["l.tokens"])
+        hidden_g, pooled = pooling(f["xl.tokens_g"])
+    embedding = torch.cat((hidden_l, hidden_g), dim=-1)
+    e1, _ = rel_err(embedding, f["xl.embedding"])
+    e2, _ = rel_err(pooled, f["xl.pooled"])
+    tol = 2e-4 if dtype == torch.float32 else 4e-2
+    print(f"\n[DoubleTextEncoder {dtype}] embedding max-abs {e1:.3e}, pooled {e2:.3e} of max|ref|")
+    assert e1 <= tol and e2 <= tol
