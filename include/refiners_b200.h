@@ -192,6 +192,9 @@ int rb200_concat_channels(void* stream, int dtype, int n, const void* const* src
  * the 2x upsampling of sampling.py:101-161 (Upsample). */
 int rb200_resize_nearest(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C,
                          int Ho, int Wo);
+/* k x k average pooling, stride k, of a channels-last map, x[B,H,W,C] -> y[B,H/k,W/k,C] (rows / columns beyond the last
+ * full window are dropped, as torch.nn.AvgPool2d does): foundationals/latent_diffusion/t2i_adapter.py:17-19 (Downsample2d). */
+int rb200_avg_pool2d(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int k);
 
 /* ---- Scaled dot-product attention -----------------------------------------------------------
  * Replaces fluxion/layers/attentions.py:115-202 (split heads, F.scaled_dot_product_attention,

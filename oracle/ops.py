@@ -83,6 +83,11 @@ def silu(x: Tensor) -> Tensor:
     return x / (1.0 + torch.exp(-x))
 
 
+def relu(x: Tensor) -> Tensor:
+    """fluxion/layers/activations.py ReLU."""
+    return torch.clamp_min(x, 0.0)
+
+
 def gelu(x: Tensor) -> Tensor:
     """Exact (erf) GeLU.  Reference: fluxion/layers/activations.py:83-114 (approximation NONE)."""
     if FAST:

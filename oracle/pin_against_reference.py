@@ -181,6 +181,58 @@ def pin_sag(write: bool) -> None:
         print(f"  wrote {GOLDEN / 'sag.safetensors'}")
 
 
+def pin_t2i(write: bool) -> None:
+    """T2I-Adapter: both condition encoders at full width on a 256x256 condition image, and the adapters injected into SD1UNet /
+    SDXLUNet (keyed weights, 32x32 latents, scale 0.8); own fixture file (the UNet inputs are keyed, only outputs are stored)."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.t2i_adapter import SD1T2IAdapter
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.t2i_adapter import SDXLT2IAdapter
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.unet import SDXLUNet
+    from safetensors.torch import save_file
+
+    from oracle import t2i as ot2i
+    from oracle import unet as ounet
+    from oracle.cases import keyed_input
+    from oracle.weights import keyed_state_dict
+
+    print("T2I-Adapter")
+    fx = {}
+    with torch.no_grad():
+        for tag, unet_cls, adapter_cls, seed in (("sd1", SD1UNet, SD1T2IAdapter, 1), ("sdxl", SDXLUNet, SDXLT2IAdapter, 2)):
+            unet = unet_cls(4)
+            usd = keyed_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=seed)
+            unet.load_state_dict(usd)
+            adapter = adapter_cls(unet, name="depth", scale=0.8)
+            esd = keyed_state_dict({k: tuple(v.shape) for k, v in adapter.condition_encoder.state_dict().items()}, seed=31)
+            adapter.condition_encoder.load_state_dict(esd)
+            adapter.inject()
+            condition = keyed_input(f"t2i.{tag}.condition", (1, 3, 256, 256))
+            features = adapter.compute_condition_features(condition)
+            mine = ot2i.condition_encoder(esd, condition, xl=(tag == "sdxl"))
+            for n, (a, b) in enumerate(zip(mine, features)):
+                _close(f"{tag} condition feature {n} {tuple(b.shape)}", a, b)
+            adapter.set_condition_features(features)
+            x, ts = keyed_input(f"t2i.{tag}.x", (1, 4, 32, 32)), torch.tensor([601.0])
+            unet.set_timestep(ts)
+            if tag == "sd1":
+                ctx = keyed_input("t2i.sd1.ctx", (1, 77, 768))
+                unet.set_clip_text_embedding(ctx)
+                y = unet(x)
+                _close("SD1UNet + T2I-Adapter", ounet.sd1_unet(usd, x, ts, ctx, t2i=(mine, 0.8)), y)
+            else:
+                ctx, pooled = keyed_input("t2i.sdxl.ctx", (1, 77, 2048)), keyed_input("t2i.sdxl.pooled", (1, 1280))
+                ids = torch.tensor([[1024.0, 1024, 0, 0, 1024, 1024]])
+                unet.set_clip_text_embedding(ctx); unet.set_pooled_text_embedding(pooled); unet.set_time_ids(ids)
+                y = unet(x)
+                _close("SDXLUNet + T2I-Adapter", ounet.sdxl_unet(usd, x, ts, ctx, pooled, ids, t2i=(mine, 0.8)), y)
+            fx[f"{tag}.y"] = y
+            fx[f"{tag}.feature_3"] = features[3]  # the coarsest map; the others are re-derived by the (pinned) oracle in the tests
+    if write:
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "t2i.safetensors"))
+        print(f"  wrote {GOLDEN / 't2i.safetensors'}")
+
+
 def pin_vae(write: bool) -> None:
     """LatentDiffusionAutoencoder.encode / decode (auto_encoder.py:305-331) on keyed weights; own fixture file."""
     _import_reference()
@@ -694,7 +746,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-vae-tiled": pin_vae_tiled, "--only-dinov2": pin_dinov2,
-        "--only-clip": pin_clip, "--only-clip-text": pin_clip_text, "--only-sag": pin_sag,
+        "--only-clip": pin_clip, "--only-clip-text": pin_clip_text, "--only-sag": pin_sag, "--only-t2i": pin_t2i,
         "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]

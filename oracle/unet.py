@@ -185,7 +185,8 @@ def sd1_controlnet(
     return deltas
 
 
-def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, residuals: list[Tensor] | None = None) -> Tensor:
+def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, residuals: list[Tensor] | None = None,
+             t2i: tuple[tuple[Tensor, ...], float] | None = None) -> Tensor:
     """SD1UNet forward (stable_diffusion_1/unet.py:165-249): 12 down entries each recording a
     skip, the middle block (added to the 13th residual slot: 0.0 for the plain UNet), 12 up entries
     each consuming one skip.  ``residuals`` are the 13 ControlNet corrections already sitting in the
@@ -204,6 +205,9 @@ def sd1_unet(sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, r
             h = residual_block(sd, p + ".ResidualBlock", h, temb)
             if entry[1]:
                 h = cross_attention_2d(sd, p + ".CLIPLCrossAttention", h, clip_text_embedding, 8, 1, False)
+        if t2i is not None and i in (2, 5, 8, 11):
+            # T2IFeatures (stable_diffusion_1/t2i_adapter.py:24-31): a Residual in front of the tap - the encoder continues from it
+            h = h + t2i[1] * t2i[0][(2, 5, 8, 11).index(i)]
         # ResidualAccumulator: residuals[n] = x + residuals[n]; the accumulator is a Passthrough, so the
         # encoder itself continues from the uncorrected h
         skips.append(h if residuals is None else h + residuals[i])
@@ -286,9 +290,10 @@ def sdxl_control_lora(
 
 def sdxl_unet(
     sd: SD, x: Tensor, timestep: Tensor, clip_text_embedding: Tensor, pooled_text_embedding: Tensor, time_ids: Tensor,
-    residuals: list[Tensor] | None = None,
+    residuals: list[Tensor] | None = None, t2i: tuple[tuple[Tensor, ...], float] | None = None,
 ) -> Tensor:
-    """SDXLUNet forward (sdxl/unet.py:258-351).  ``residuals``: the 10 ControlLora corrections already sitting
+    """SDXLUNet forward (sdxl/unet.py:258-351).  ``t2i`` = (the four T2I-Adapter feature maps, scale): added in front of the
+    taps of encoder entries 3, 5, 8 and at the end of the middle block (stable_diffusion_xl/t2i_adapter.py:25-40).  ``residuals``: the 10 ControlLora corrections already sitting
     in the residual slots when the UNet runs (the control copy is child 0 of the UNet, control_lora.py:283-286)."""
     dtype = x.dtype
     temb = sdxl_timestep_embedding(sd, timestep, pooled_text_embedding, time_ids, dtype)
@@ -304,11 +309,15 @@ def sdxl_unet(
             h = residual_block(sd, p + ".ResidualBlock", h, temb)
             if entry[1]:
                 h = cross_attention_2d(sd, p + ".SDXLCrossAttention", h, clip_text_embedding, entry[2], entry[1], True)
+        if t2i is not None and i in (3, 5, 8):
+            h = h + t2i[1] * t2i[0][(3, 5, 8).index(i)]
         skips.append(h if residuals is None else h + residuals[i])  # ResidualAccumulator is a Passthrough
     m = "MiddleBlock"
     h = residual_block(sd, m + ".ResidualBlock_1", h, temb)
     h = cross_attention_2d(sd, m + ".SDXLCrossAttention", h, clip_text_embedding, 20, 10, True)
     h = residual_block(sd, m + ".ResidualBlock_2", h, temb)
+    if t2i is not None:
+        h = h + t2i[1] * t2i[0][3]
     # Residual(UseContext residuals[-1]): the spare 10th slot keeps its initial 0.0 unless ControlLora wrote it
     h = h + (0.0 if residuals is None else residuals[9])
     for n, (layers, heads, up) in enumerate(_SDXL_UP):

@@ -101,6 +101,7 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_pad_channels": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _L, _L, _L, _L]),
     "rb200_concat_channels": (_I, [_P, _I, _I, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _P, _L]),
     "rb200_resize_nearest": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
+    "rb200_avg_pool2d": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I]),
     "rb200_window_partition": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
 }
 
@@ -980,6 +981,21 @@ def concat_channels(parts: Sequence[Tensor]) -> Tensor:
 
 def resize_nearest_supported(x: Tensor) -> bool:
     return x.is_cuda and x.ndim == 4 and x.dtype in _DT and x.shape[1] % (16 // x.element_size()) == 0
+
+
+def avg_pool2d(x: Tensor, k: int) -> Tensor:
+    """k x k average pooling with stride k of an NCHW map (result channels-last); see rb200_avg_pool2d."""
+    _inference_only(x)
+    lib = load_library()
+    B, C, H, W = x.shape
+    if C % (16 // x.element_size()):
+        raise BackendError(f"avg_pool2d: {C} channels are not a whole number of 16-byte vectors")
+    xc = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, C, H // k, W // k), device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    if y.numel():
+        with torch.cuda.device(x.device):
+            _check(lib.rb200_avg_pool2d(_stream(), _dtype_code(x), xc.data_ptr(), y.data_ptr(), B, H, W, C, int(k)))
+    return y
 
 
 def resize_nearest(x: Tensor, height: int, width: int) -> Tensor:

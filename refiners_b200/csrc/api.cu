@@ -54,6 +54,7 @@ int window_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, i
 int pad_channels_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int64_t, int64_t, int64_t, int64_t);
 int concat_channels_impl(cudaStream_t, int, int, const void* const*, const int*, void*, int64_t);
 int resize_nearest_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
+int avg_pool_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int);
 int conv_pack_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int, int);
 int geglu_pack_impl(cudaStream_t, int, const void*, const void*, void*, void*, int64_t, int64_t);
 int lora_pack_impl(cudaStream_t, int, int, const rb200_lora*, int64_t, int64_t, void*, void*, float*, int);
@@ -249,6 +250,13 @@ int rb200_concat_channels(void* stream, int dtype, int n, const void* const* src
   if (bad_dtype(dtype) || !srcs || !channels || !y) RB200_FAIL(-1, "concat_channels: bad arguments");
   if (pixels <= 0) return 0;
   return concat_channels_impl(static_cast<cudaStream_t>(stream), dtype, n, srcs, channels, y, pixels);
+}
+
+int rb200_avg_pool2d(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int k) {
+  if (bad_dtype(dtype) || !x || !y) RB200_FAIL(-1, "avg_pool2d: bad arguments");
+  if (k < 1 || H < k || W < k || C < 1) RB200_FAIL(-1, "avg_pool2d: bad geometry");
+  if (B <= 0) return 0;
+  return avg_pool_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, H, W, C, k);
 }
 
 int rb200_resize_nearest(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int Ho, int Wo) {

@@ -422,6 +422,38 @@ __global__ void resize_nearest_kernel(const T* __restrict__ x, T* __restrict__ y
   }
 }
 
+// k x k average pooling with stride k of a dense NHWC map (T2I-Adapter's Downsample2d); fp32 sum in raster order of the
+// window, one rounding.  One thread per output pixel-vector of 16 bytes.
+template <typename T>
+__global__ void avg_pool_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t B, int H, int W, int C, int k) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V, Ho = H / k, Wo = W / k;
+  const int64_t total = B * Ho * Wo * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const float inv = 1.0f / float(k * k);
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int v = int(idx % cv);
+    int64_t t = idx / cv;
+    const int wo = int(t % Wo);
+    t /= Wo;
+    const int ho = int(t % Ho);
+    const int64_t b = t / Ho;
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        const Vec16<T> in = ld16(x + ((b * H + ho * k + dy) * W + wo * k + dx) * C + v * V);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] += to_f(in.v[e]);
+      }
+    Vec16<T> out;
+#pragma unroll
+    for (int e = 0; e < V; ++e) out.v[e] = from_f<T>(acc[e] * inv);
+    st16(y + idx * V, out);
+  }
+}
+
 // Channel padding for the tensor-core conv (needs Cin % 8 == 0): y[b, h, w, 0..Cp) = x[b, 0..C, h, w] then zeros.
 // x is addressed through element strides (NCHW or channels-last), y is dense NHWC; one thread per output pixel-vector.
 template <typename T>
@@ -769,6 +801,17 @@ int resize_nearest_impl(cudaStream_t st, int dtype, const void* x, void* y, int6
                                                                              float(W) / float(Wo));
   });
   RB200_CHECK_LAUNCH("resize_nearest");
+  return 0;
+}
+
+int avg_pool_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int k) {
+  if (!aligned16(x) || !aligned16(y)) RB200_FAIL(-1, "avg_pool2d: buffers must be 16-byte aligned");
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    if (C % V != 0) RB200_FAIL(-1, "avg_pool2d: C=%d must be a multiple of %d", C, V);
+    avg_pool_kernel<T><<<ew_grid(B * (H / k) * (W / k) * (C / V)), 256, 0, st>>>((const T*)x, (T*)y, B, H, W, C, k);
+  });
+  RB200_CHECK_LAUNCH("avg_pool2d");
   return 0;
 }
 

@@ -211,23 +211,29 @@ def test_clip_text_encoder_gpu(cuda_device, dtype):
     assert e_rms <= t_rms + 1e-3 and e_max <= 1.25 * t_max + 1e-3
 
 
+def double_encode(double, f, device="cpu"):
+    pooling = double.layer(("Parallel", "TextEncoderWithPooling"), fl.Chain)
+    assert pooling.tokenizer.pad_token_id == 0  # the bigG tower pads with 0: its end-of-text position is unique
+    l_branch = double.layer(("Parallel", "CLIPTextEncoderL"), fl.Chain)
+    with no_grad():
+        hidden_l = l_branch(f["l.tokens"])
+        hidden_g, pooled = pooling(f["xl.tokens_g"])
+    return torch.cat((hidden_l, hidden_g), dim=-1), pooled
+
+
+def test_sdxl_double_text_encoder_host():
+    f = load_file(str(GOLDEN / "clip_text.safetensors"))
+    embedding, pooled = double_encode(double_tower("cpu", torch.float32), f)
+    assert rel_err(embedding, f["xl.embedding"])[0] <= 1e-5 and rel_err(pooled, f["xl.pooled"])[0] <= 1e-5
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
 def test_sdxl_double_text_encoder_gpu(cuda_device, dtype):
     """SDXL's DoubleTextEncoder (L + bigG towers at their penultimate layer, pooled + projected bigG embedding) on recorded
     token ids: the L tower's ids go in, the bigG tokenizer differs only in its padding id, so its ids are substituted."""
     f = load_file(str(GOLDEN / "clip_text.safetensors"))
-    double = double_tower(cuda_device, dtype)
-    from refiners_b200.foundationals.clip import CLIPTextEncoderG, CLIPTokenizer
-
-    g_tokenizer = double.ensure_find(CLIPTextEncoderG).ensure_find(CLIPTokenizer) if double.find(CLIPTextEncoderG) else None
-    assert g_tokenizer is not None and g_tokenizer.pad_token_id == 0
-    pooling = double.layer(("Parallel", "TextEncoderWithPooling"), fl.Chain)
-    l_branch = double.layer(("Parallel", "CLIPTextEncoderL"), fl.Chain)
-    with no_grad():
-        hidden_l = l_branch(f["l.tokens"])
-        hidden_g, pooled = pooling(f["xl.tokens_g"])
-    embedding = torch.cat((hidden_l, hidden_g), dim=-1)
+    embedding, pooled = double_encode(double_tower(cuda_device, dtype), f)
     e1, _ = rel_err(embedding, f["xl.embedding"])
     e2, _ = rel_err(pooled, f["xl.pooled"])
     tol = 2e-4 if dtype == torch.float32 else 4e-2
