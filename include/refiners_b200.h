@@ -220,6 +220,19 @@ int rb200_attention_probs(void* stream, int dtype, const void* q, const void* k,
                           int H, int64_t Sq, int64_t Sk, int D, int64_t q_sb, int64_t q_ss,
                           int64_t k_sb, int64_t k_ss, float scale);
 
+/* ---- StyleAligned shared attention -------------------------------------------------------------
+ * Replaces one `StyleAligned` chain of foundationals/latent_diffusion/style_aligned.py:136-207 (Parallel(Identity,
+ * ExtractReferenceFeatures) -> AdaIN :47-92 -> ScaleReferenceFeatures :95-133 -> Concatenate) applied to q, k or v of a
+ * classifier-free-guidance batch.  x: [B, S, C] with element strides (x_sb, x_ss) - a slice of a fused q/k/v projection is
+ * read in place; y: contiguous [B, S or 2S, C].  ref(b) = first image of b's half of the batch:
+ *   y[b, s < S] = adain ? (x[b,s] - mean[b]) / (std[b] + eps) * std[ref(b)] + mean[ref(b)] : x[b,s]
+ *   y[b, S + s] = x[ref(b), s] * (b == ref(b) ? 1 : scale)                   (rows present only when concatenate != 0)
+ * mean / std: per (image, channel) over the S tokens, std unbiased; ws: rb200_style_aligned_workspace_bytes(B, C). */
+size_t rb200_style_aligned_workspace_bytes(int64_t B, int64_t C);
+int rb200_style_aligned(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t S, int64_t C,
+                        int64_t x_sb, int64_t x_ss, int adain, int concatenate, float scale, float eps,
+                        void* ws, size_t ws_bytes);
+
 /* ---- SAM decomposed relative-position attention ---------------------------------------------
  * Replaces foundationals/segment_anything/image_encoder.py:87-127 (RelativePositionAttention):
  *   logits = (q * d^-1/2) k^T + rel_h[:, :, None] + rel_w[:, None, :], softmax, @ v

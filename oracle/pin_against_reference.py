@@ -233,6 +233,49 @@ def pin_t2i(write: bool) -> None:
         print(f"  wrote {GOLDEN / 't2i.safetensors'}")
 
 
+def pin_style_aligned(write: bool) -> None:
+    """StyleAligned on SD1UNet and SDXLUNet (keyed weights, guidance batch of 2 x 2 images at 32x32 latents, scale 0.7); own
+    fixture file (inputs are keyed, only outputs are stored)."""
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+    from refiners.foundationals.latent_diffusion.stable_diffusion_xl.unet import SDXLUNet
+    from refiners.foundationals.latent_diffusion.style_aligned import StyleAlignedAdapter
+    from safetensors.torch import save_file
+
+    from oracle import unet as ounet
+    from oracle.cases import keyed_input
+    from oracle.weights import keyed_state_dict
+
+    print("StyleAligned")
+    fx = {}
+    with torch.no_grad():
+        for tag, unet_cls, seed, width in (("sd1", SD1UNet, 1, 768), ("sdxl", SDXLUNet, 2, 2048)):
+            unet = unet_cls(4)
+            usd = keyed_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=seed)
+            unet.load_state_dict(usd)
+            StyleAlignedAdapter(unet, scale=0.7).inject()
+            x, ts = keyed_input(f"style.{tag}.x", (4, 4, 32, 32)), torch.tensor([601.0])
+            ctx = keyed_input(f"style.{tag}.ctx", (4, 77, width))
+            unet.set_timestep(ts); unet.set_clip_text_embedding(ctx)
+            ounet.style_aligned_scale = 0.7
+            try:
+                if tag == "sd1":
+                    y = unet(x)
+                    mine = ounet.sd1_unet(usd, x, ts, ctx)
+                else:
+                    pooled, ids = keyed_input("style.sdxl.pooled", (4, 1280)), torch.tensor([[1024.0, 1024, 0, 0, 1024, 1024]] * 4)
+                    unet.set_pooled_text_embedding(pooled); unet.set_time_ids(ids)
+                    y = unet(x)
+                    mine = ounet.sdxl_unet(usd, x, ts, ctx, pooled, ids)
+            finally:
+                ounet.style_aligned_scale = None
+            _close(f"{tag} UNet + StyleAligned", mine, y)
+            fx[f"{tag}.y"] = y
+    if write:
+        save_file({k: v.contiguous() for k, v in fx.items()}, str(GOLDEN / "style_aligned.safetensors"))
+        print(f"  wrote {GOLDEN / 'style_aligned.safetensors'}")
+
+
 def pin_vae(write: bool) -> None:
     """LatentDiffusionAutoencoder.encode / decode (auto_encoder.py:305-331) on keyed weights; own fixture file."""
     _import_reference()
@@ -746,7 +789,7 @@ if __name__ == "__main__":
     write = "--check" not in sys.argv
     sections = {
         "--only-controlnet": pin_controlnet, "--only-step": pin_denoise_step, "--only-vae": pin_vae, "--only-vae-tiled": pin_vae_tiled, "--only-dinov2": pin_dinov2,
-        "--only-clip": pin_clip, "--only-clip-text": pin_clip_text, "--only-sag": pin_sag, "--only-t2i": pin_t2i,
+        "--only-clip": pin_clip, "--only-clip-text": pin_clip_text, "--only-sag": pin_sag, "--only-t2i": pin_t2i, "--only-style-aligned": pin_style_aligned,
         "--only-full-size": pin_full_size,
     }
     chosen = [fn for flag, fn in sections.items() if flag in sys.argv]

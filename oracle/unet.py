@@ -80,11 +80,37 @@ def residual_block(sd: SD, prefix: str, x: Tensor, temb: Tensor, eps: float = 1e
 middle_probe: dict | None = None
 
 
+# StyleAligned (style_aligned.py:136-265): when ``style_aligned_scale`` is a float, every SELF-attention shares the first
+# image of each guidance half: q, k are moved to its per-channel token statistics, k and v get its (scaled) rows appended.
+style_aligned_scale: float | None = None
+
+
+def _style_aligned(q: Tensor, k: Tensor, v: Tensor, scale: float, eps: float = 1e-8) -> tuple[Tensor, Tensor, Tensor]:
+    half = q.shape[0] // 2
+
+    def reference(x: Tensor) -> Tensor:  # ExtractReferenceFeatures :13-44
+        return torch.stack((x[0], x[half])).repeat_interleave(half, dim=0)
+
+    def adain(x: Tensor, ref: Tensor) -> Tensor:  # :47-92 (torch.std: unbiased)
+        mean, std = x.mean(dim=-2, keepdim=True), x.std(dim=-2, keepdim=True)
+        return (x - mean) / (std + eps) * ref.std(dim=-2, keepdim=True) + ref.mean(dim=-2, keepdim=True)
+
+    def scaled(ref: Tensor) -> Tensor:  # ScaleReferenceFeatures :95-133: every image but the first of its half
+        factor = torch.full((q.shape[0], 1, 1), scale, dtype=ref.dtype, device=ref.device)
+        factor[0], factor[half] = 1.0, 1.0
+        return ref * factor
+
+    rq, rk, rv = reference(q), reference(k), reference(v)
+    return adain(q, rq), torch.cat((adain(k, rk), scaled(rk)), dim=-2), torch.cat((v, scaled(rv)), dim=-2)
+
+
 def attention(sd: SD, prefix: str, q_in: Tensor, kv_in: Tensor, heads: int) -> Tensor:
     """fl.Attention: Distribute(Wq, Wk, Wv) -> SDPA -> Wo  (fluxion/layers/attentions.py:205-316)."""
     q = _lin(sd, prefix + ".Distribute.Linear_1", q_in)
     k = _lin(sd, prefix + ".Distribute.Linear_2", kv_in)
     v = _lin(sd, prefix + ".Distribute.Linear_3", kv_in)
+    if style_aligned_scale is not None and prefix.endswith(".SelfAttention"):
+        q, k, v = _style_aligned(q, k, v, style_aligned_scale)
     if middle_probe is not None and "MiddleBlock" in prefix and prefix.endswith(".SelfAttention") and "map" not in middle_probe:
         split = lambda t: t.reshape(t.shape[0], t.shape[1], heads, -1).transpose(1, 2)  # noqa: E731
         qh, kh = split(q), split(k)

@@ -102,6 +102,8 @@ _SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "rb200_concat_channels": (_I, [_P, _I, _I, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int), _P, _L]),
     "rb200_resize_nearest": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
     "rb200_avg_pool2d": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I]),
+    "rb200_style_aligned_workspace_bytes": (_Z, [_L, _L]),
+    "rb200_style_aligned": (_I, [_P, _I, _P, _P, _L, _L, _L, _L, _L, _I, _I, _F, _F, _P, _Z]),
     "rb200_window_partition": (_I, [_P, _I, _P, _P, _L, _I, _I, _I, _I, _I]),
 }
 
@@ -981,6 +983,23 @@ def concat_channels(parts: Sequence[Tensor]) -> Tensor:
 
 def resize_nearest_supported(x: Tensor) -> bool:
     return x.is_cuda and x.ndim == 4 and x.dtype in _DT and x.shape[1] % (16 // x.element_size()) == 0
+
+
+def style_aligned(x: Tensor, *, adain: bool, concatenate: bool, scale: float, epsilon: float) -> Tensor:
+    """One `StyleAligned` chain on q, k or v ``[B, S, C]`` of a guidance batch -> ``[B, S or 2S, C]``; see rb200_style_aligned."""
+    _inference_only(x)
+    lib = load_library()
+    B, S, C = x.shape
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    y = torch.empty((B, 2 * S if concatenate else S, C), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.rb200_style_aligned_workspace_bytes(B, C) if adain else 0
+        ws = torch.empty(max(ws_bytes, 1), device=x.device, dtype=torch.uint8)
+        if y.numel():
+            _check(lib.rb200_style_aligned(_stream(), _dtype_code(x), x.data_ptr(), y.data_ptr(), B, S, C, x.stride(0), x.stride(1),
+                                           int(adain), int(concatenate), float(scale), float(epsilon), ws.data_ptr(), ws_bytes))
+    return y
 
 
 def avg_pool2d(x: Tensor, k: int) -> Tensor:

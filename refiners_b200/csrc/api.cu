@@ -55,6 +55,7 @@ int pad_channels_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, 
 int concat_channels_impl(cudaStream_t, int, int, const void* const*, const int*, void*, int64_t);
 int resize_nearest_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int, int);
 int avg_pool_impl(cudaStream_t, int, const void*, void*, int64_t, int, int, int, int);
+int style_aligned_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float, float, float*);
 int conv_pack_impl(cudaStream_t, int, const void*, void*, int64_t, int64_t, int, int);
 int geglu_pack_impl(cudaStream_t, int, const void*, const void*, void*, void*, int64_t, int64_t);
 int lora_pack_impl(cudaStream_t, int, int, const rb200_lora*, int64_t, int64_t, void*, void*, float*, int);
@@ -250,6 +251,18 @@ int rb200_concat_channels(void* stream, int dtype, int n, const void* const* src
   if (bad_dtype(dtype) || !srcs || !channels || !y) RB200_FAIL(-1, "concat_channels: bad arguments");
   if (pixels <= 0) return 0;
   return concat_channels_impl(static_cast<cudaStream_t>(stream), dtype, n, srcs, channels, y, pixels);
+}
+
+size_t rb200_style_aligned_workspace_bytes(int64_t B, int64_t C) { return size_t(B) * size_t(C) * 2 * sizeof(float); }
+
+int rb200_style_aligned(void* stream, int dtype, const void* x, void* y, int64_t B, int64_t S, int64_t C, int64_t x_sb, int64_t x_ss, int adain,
+                        int concatenate, float scale, float eps, void* ws, size_t ws_bytes) {
+  if (bad_dtype(dtype) || !x || !y) RB200_FAIL(-1, "style_aligned: bad arguments");
+  if (B <= 0 || S <= 0 || C <= 0) return 0;
+  if (B % 2 != 0) RB200_FAIL(-1, "style_aligned: the batch (%lld) must be the two halves of a classifier-free-guidance batch", (long long)B);
+  if (adain && (!ws || ws_bytes < rb200_style_aligned_workspace_bytes(B, C))) RB200_FAIL(-1, "style_aligned: workspace too small");
+  return style_aligned_impl(static_cast<cudaStream_t>(stream), dtype, x, y, B, S, C, x_sb, x_ss, adain, concatenate, scale, eps,
+                            static_cast<float*>(ws));
 }
 
 int rb200_avg_pool2d(void* stream, int dtype, const void* x, void* y, int64_t B, int H, int W, int C, int k) {

@@ -712,6 +712,115 @@ int add_impl(cudaStream_t st, int dtype, const void* a, const void* b, void* y, 
   return 0;
 }
 
+// ------------------------------------------------------------------------------ StyleAligned (shared attention)
+// foundationals/latent_diffusion/style_aligned.py:13-207 of the reference, for one of q / k / v [B, S, C] of a guidance batch
+// (two halves of B / 2 images; ref(b) = first image of b's half):
+//   y[b, s < S]      = adain ? (x[b, s] - mean[b]) / (std[b] + eps) * std[ref(b)] + mean[ref(b)] : x[b, s]
+//   y[b, S + s]      = x[ref(b), s] * (b == ref(b) ? 1 : scale)                                   (only when concatenating)
+// with mean / std per (image, channel) over the S tokens (std unbiased, as torch.std).  Statistics in fp32, two passes over
+// rows that stay in L2; the apply pass rounds once.
+template <typename T>
+__global__ void __launch_bounds__(256) token_stats_kernel(const T* __restrict__ x, float* __restrict__ stats, int64_t S, int C,
+                                                          int64_t x_sb, int64_t x_ss) {
+  constexpr int V = 16 / sizeof(T);
+  constexpr int CH_THREADS = 8;             // 8 threads x V channels per row chunk
+  constexpr int ROWS = 256 / CH_THREADS;    // 32 row lanes
+  __shared__ float red[ROWS][CH_THREADS * V];
+  __shared__ float mean_s[CH_THREADS * V];
+  const int ct = threadIdx.x % CH_THREADS, rl = threadIdx.x / CH_THREADS;
+  const int c0 = (blockIdx.x * CH_THREADS + ct) * V;
+  const int64_t b = blockIdx.y;
+  const bool live = c0 < C;
+  const T* base = x + b * x_sb + c0;
+  float acc[V];
+  auto reduce_rows = [&](float (&a)[V]) {  // sum over the 32 row lanes, result in red[0]
+#pragma unroll
+    for (int e = 0; e < V; ++e) red[rl][ct * V + e] = a[e];
+    __syncthreads();
+    for (int h = ROWS / 2; h > 0; h >>= 1) {
+      if (rl < h) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) red[rl][ct * V + e] += red[rl + h][ct * V + e];
+      }
+      __syncthreads();
+    }
+  };
+#pragma unroll
+  for (int e = 0; e < V; ++e) acc[e] = 0.f;
+  if (live)
+    for (int64_t r = rl; r < S; r += ROWS) {
+      const Vec16<T> v = ld16(base + r * x_ss);
+#pragma unroll
+      for (int e = 0; e < V; ++e) acc[e] += to_f(v.v[e]);
+    }
+  reduce_rows(acc);
+  if (rl == 0) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) mean_s[ct * V + e] = red[0][ct * V + e] / float(S);
+  }
+  __syncthreads();
+  float mu[V];
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    mu[e] = mean_s[ct * V + e];
+    acc[e] = 0.f;
+  }
+  if (live)
+    for (int64_t r = rl; r < S; r += ROWS) {
+      const Vec16<T> v = ld16(base + r * x_ss);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float d = to_f(v.v[e]) - mu[e];
+        acc[e] = fmaf(d, d, acc[e]);
+      }
+    }
+  reduce_rows(acc);
+  if (rl == 0 && live) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      stats[(b * C + c0 + e) * 2 + 0] = mu[e];
+      stats[(b * C + c0 + e) * 2 + 1] = sqrtf(red[0][ct * V + e] / float(S > 1 ? S - 1 : 1));
+    }
+  }
+}
+
+template <typename T>
+__global__ void style_aligned_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats, int64_t B, int64_t S,
+                                           int C, int64_t x_sb, int64_t x_ss, int adain, int concatenate, float scale, float eps) {
+  constexpr int V = 16 / sizeof(T);
+  const int cv = C / V;
+  const int64_t S_out = concatenate ? 2 * S : S, half = B / 2;
+  const int64_t total = B * S_out * cv;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int v = int(idx % cv);
+    int64_t t = idx / cv;
+    const int64_t so = t % S_out, b = t / S_out;
+    const int64_t ref = (b / half) * half;
+    Vec16<T> out;
+    if (so < S) {
+      const Vec16<T> in = ld16(x + b * x_sb + so * x_ss + v * V);
+      if (adain) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int c = v * V + e;
+          const float m = stats[(b * C + c) * 2], sd = stats[(b * C + c) * 2 + 1];
+          const float rm = stats[(ref * C + c) * 2], rs = stats[(ref * C + c) * 2 + 1];
+          out.v[e] = from_f<T>((to_f(in.v[e]) - m) / (sd + eps) * rs + rm);
+        }
+      } else {
+        out = in;
+      }
+    } else {
+      const Vec16<T> in = ld16(x + ref * x_sb + (so - S) * x_ss + v * V);
+      const float k = b == ref ? 1.0f : scale;
+#pragma unroll
+      for (int e = 0; e < V; ++e) out.v[e] = from_f<T>(to_f(in.v[e]) * k);
+    }
+    st16(y + idx * V, out);
+  }
+}
+
 // ---------------------------------------------------------------- denoising-step glue (CFG + Euler)
 // The reference evaluates these with one ATen kernel per arithmetic operator, each rounding its result to the tensor
 // dtype (model.py:137-159, solvers/euler.py:63-100).  The fused kernels reproduce that rounding sequence (`rn<T>`), so
@@ -801,6 +910,27 @@ int resize_nearest_impl(cudaStream_t st, int dtype, const void* x, void* y, int6
                                                                              float(W) / float(Wo));
   });
   RB200_CHECK_LAUNCH("resize_nearest");
+  return 0;
+}
+
+int style_aligned_impl(cudaStream_t st, int dtype, const void* x, void* y, int64_t B, int64_t S, int64_t C, int64_t x_sb, int64_t x_ss, int adain,
+                       int concatenate, float scale, float eps, float* stats) {
+  if (!aligned16(x) || !aligned16(y)) RB200_FAIL(-1, "style_aligned: buffers must be 16-byte aligned");
+  if (B > 65535) RB200_FAIL(-1, "style_aligned: batch %lld too large", (long long)B);
+  DISPATCH_T(dtype, {
+    constexpr int V = 16 / sizeof(T);
+    if (C % V != 0 || (x_sb * sizeof(T)) % 16 != 0 || (x_ss * sizeof(T)) % 16 != 0)
+      RB200_FAIL(-1, "style_aligned: channels and strides must be whole 16-byte vectors");
+    if (adain) {
+      dim3 grid(unsigned(ceil_div(C, 8 * V)), unsigned(B));
+      token_stats_kernel<T><<<grid, 256, 0, st>>>((const T*)x, stats, S, int(C), x_sb, x_ss);
+    }
+    const int64_t S_out = concatenate ? 2 * S : S;
+    style_aligned_apply_kernel<T><<<ew_grid(B * S_out * (C / V)), 256, 0, st>>>((const T*)x, (T*)y, stats, B, S, int(C), x_sb, x_ss, adain,
+                                                                               concatenate, scale, eps);
+  });
+  RB200_CHECK_LAUNCH("style_aligned");
+  if (adain) count_launch();
   return 0;
 }
 
