@@ -310,6 +310,7 @@ int rb200_sdpa(void* stream, int dtype, const void* q, const void* k, const void
   p.k2 = k2; p.v2 = v2; p.Sk2 = Sk2; p.k2_sb = k2_sb; p.k2_ss = k2_ss; p.v2_sb = v2_sb; p.v2_ss = v2_ss; p.scale2 = scale2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (kernel_mode() != 1) {
+    if (tc_sdpa_short_supported(p)) return tc_sdpa_short(st, p);
     if (tc_sdpa2_supported(p)) return tc_sdpa2(st, p);
     if (tc_sdpa_supported(p)) return tc_sdpa(st, p);
   }

@@ -163,5 +163,8 @@ int tc_sdpa(cudaStream_t st, const SdpaProblem& p);
 // second-generation kernel (tc_attention2.cu): head dim <= 64, one K/V set, no bias, Sq > 128
 bool tc_sdpa2_supported(const SdpaProblem& p);
 int tc_sdpa2(cudaStream_t st, const SdpaProblem& p);
+// single-pass kernel for short key sequences (tc_attention_short.cu): Sk <= 128, head dim <= 64, one K/V set, no bias
+bool tc_sdpa_short_supported(const SdpaProblem& p);
+int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p);
 
 }  // namespace rb200

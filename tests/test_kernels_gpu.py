@@ -640,6 +640,36 @@ def test_sdpa_growing_maxima(cuda_device, dtype, shape):
     assert_close(y, ref, dtype, scale=4.0, what=f"sdpa growing maxima {shape}")
 
 
+SHORT_SDPA = [
+    # (B, H, Sq, Sk, D): the single-pass short-key kernel (Sk <= 128, D <= 64) at its chunk boundaries and with ragged tiles
+    (1, 1, 1, 1, 8), (2, 3, 127, 16, 64), (2, 3, 129, 17, 40), (1, 2, 300, 32, 64), (1, 2, 256, 33, 64), (3, 2, 130, 64, 16),
+    (1, 4, 128, 65, 64), (2, 2, 500, 77, 64), (1, 2, 384, 96, 64), (1, 2, 384, 97, 64), (2, 1, 200, 127, 48), (1, 3, 260, 128, 64),
+    (8, 20, 1024, 77, 64),  # many items per CTA: the three-stage ring and both softmax groups wrap around several times
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("case", SHORT_SDPA, ids=str)
+def test_sdpa_short_keys(cuda_device, dtype, case):
+    """tc_sdpa_short_kernel against fp32 attention on the same (rounded) operands, plus: strided q / k / v views of fused
+    projections are read in place, the result is deterministic, and it agrees with the first-generation flash kernel."""
+    import os
+
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    Bn, H, Sq, Sk, D = case
+    dev = lambda t: t.to(cuda_device, dtype)
+    q, k, v = dev(_gen((Bn, Sq, H * D), 370)), dev(_gen((Bn, Sk, H * D), 371) * 1.5), dev(_gen((Bn, Sk, H * D), 372))
+    with torch.no_grad():
+        y = B.sdpa(q, k, v, H)
+        ref = _sdpa_ref(q.float(), k.float(), v.float(), H)
+        assert torch.equal(y, B.sdpa(q, k, v, H))
+        kv = torch.cat((k, v), dim=-1)  # the fused K / V projection of a cross-attention
+        assert torch.equal(y, B.sdpa(q, kv[..., : H * D], kv[..., H * D :], H))
+    assert_close(y, ref, dtype, scale=4.0, what=f"short sdpa{case}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES, ids=str)
 @pytest.mark.parametrize("guided", [True, False], ids=["cfg", "plain"])
 def test_cfg_euler_glue_is_bit_identical_to_the_operator_sequence(cuda_device, dtype, guided):
