@@ -52,6 +52,12 @@ struct ShortParams {
   int kv_bytes;         // a K (or V) tile: 16 * ksteps rows of 128 B (the TMA box of the K / V maps)
   int stage_bytes;      // TILE_BYTES + 2 * kv_bytes
   int nst;              // stages that fit the ring: 3 or 4
+  // second key / value set (IP-Adapter, DUAL instantiations): o += scale2 * softmax(q k2^T * scale) v2
+  int64_t Sk2;
+  int ksteps2;          // ceil(Sk2 / 16) <= 2
+  int kv2_bytes;        // 16 * ksteps2 rows of 128 B
+  float scale2;
+  uint32_t idesc_qk2;
   float scale_log2e;
   uint32_t idesc_qk, idesc_pv;
   int d_out;
@@ -68,10 +74,11 @@ template <> __device__ __forceinline__ uint32_t pack2s<__half>(float a, float b)
 }
 
 // NC = 32-column chunks of logits per row (Sk <= 32 * NC)
-template <typename T, int NC>
+template <typename T, int NC, bool DUAL>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                     const __grid_constant__ CUtensorMap map_v, const ShortParams p) {
+                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
+                     const __grid_constant__ CUtensorMap map_v2, const ShortParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sStage = smem;                                  // [nst][Q | K | V]
@@ -128,6 +135,10 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tma_load_4d(dst, &map_q, &full[st], 0, h, qt * QT, b);
         tma_load_4d(dst + TILE_BYTES, &map_k, &full[st], 0, h, 0, b);
         tma_load_4d(dst + TILE_BYTES + p.kv_bytes, &map_v, &full[st], 0, h, 0, b);
+        if constexpr (DUAL) {
+          tma_load_4d(dst + TILE_BYTES + 2 * p.kv_bytes, &map_k2, &full[st], 0, h, 0, b);
+          tma_load_4d(dst + TILE_BYTES + 2 * p.kv_bytes + p.kv2_bytes, &map_v2, &full[st], 0, h, 0, b);
+        }
         if (++st == nst) {
           st = 0;
           ph ^= 1;
@@ -151,6 +162,11 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const uint64_t dq = desc_kmajor(base), dk = desc_kmajor(base + TILE_BYTES);
 #pragma unroll
         for (int s = 0; s < HD / 16; ++s) umma_f16(tmem_base + g * 128, dq + uint64_t(s * 2), dk + uint64_t(s * 2), p.idesc_qk, s > 0);
+        if constexpr (DUAL) {  // S2_g = Q K2^T into its own 32 columns
+          const uint64_t dk2 = desc_kmajor(base + TILE_BYTES + 2 * p.kv_bytes);
+#pragma unroll
+          for (int s = 0; s < HD / 16; ++s) umma_f16(tmem_base + 384 + g * 32, dq + uint64_t(s * 2), dk2 + uint64_t(s * 2), p.idesc_qk2, s > 0);
+        }
         umma_commit(&bar_s[g]);
         if (++s_st == nst) {
           s_st = 0;
@@ -173,6 +189,15 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const uint64_t dp = desc_kmajor(pbase + (s >> 2) * P_SLAB) + uint64_t((s & 3) * 2);
           const uint64_t dv = desc_mnmajor(vbase, uint32_t(p.kv_bytes)) + uint64_t(s * 128);
           umma_f16(tmem_base + 256 + g * 64, dp, dv, p.idesc_pv, s > 0 ? 1u : 0u);
+        }
+        if constexpr (DUAL) {  // += P2' V2: P2' sits in the P buffer right behind the key steps of P
+          const uint32_t v2base = vbase + p.kv_bytes + p.kv2_bytes;
+          for (int s2 = 0; s2 < p.ksteps2; ++s2) {
+            const int s = p.ksteps + s2;
+            const uint64_t dp = desc_kmajor(pbase + (s >> 2) * P_SLAB) + uint64_t((s & 3) * 2);
+            const uint64_t dv = desc_mnmajor(v2base, uint32_t(p.kv2_bytes)) + uint64_t(s2 * 128);
+            umma_f16(tmem_base + 256 + g * 64, dp, dv, p.idesc_pv, 1u);
+          }
         }
         umma_commit(&empty[st]);
         umma_commit(&bar_o[g]);
@@ -247,6 +272,14 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
           for (int e = 0; e < 32; ++e) s[c * 32 + e] = __uint_as_float(raw[c][e]);
       }
+      float s2[DUAL ? 32 : 1];
+      if constexpr (DUAL) {
+        uint32_t raw2[32];
+        tmem_ld_32x32(tmem_base + 384 + g * 32 + lane_off, raw2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) s2[e] = __uint_as_float(raw2[e]);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_a(a_sfree);
@@ -280,11 +313,42 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       float l0, l1;
       f32x2_split(add_f32x2(sum_a, sum_b), l0, l1);
+      // second key set: its own softmax; o = (P V + P2' V2) / l with P2' = p2 * scale2 * l / l2, so that ONE accumulator and
+      // one 1 / l in the epilogue serve both terms
+      uint32_t pk2[DUAL ? 16 : 1];
+      if constexpr (DUAL) {
+        const int sk2 = int(p.Sk2);
+        float mm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (e >= sk2) s2[e] = -INFINITY;
+          mm = fmaxf(mm, s2[e]);
+        }
+        const float mb2 = mm * p.scale_log2e;
+        float l2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          s2[e] = ex2_approx(fmaf(s2[e], p.scale_log2e, -mb2));
+          l2 += s2[e];
+        }
+        const float f = p.scale2 * (l0 + l1) / l2;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) pk2[e / 2] = pack2s<T>(s2[e] * f, s2[e + 1] * f);
+      }
       // P_g is free once P V of the group's previous item has completed - which is also when its output can be read
       if (k > 0) flush(k - 1);
 #pragma unroll
       for (int c = 0; c < NC * 4; ++c)  // 16-byte chunks of 8 keys
         st_shared_v4(prow + (c >> 3) * P_SLAB + ((uint32_t(c & 7) << 4) ^ swz), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      if constexpr (DUAL) {
+#pragma unroll
+        for (int c2 = 0; c2 < 4; ++c2) {  // P2' behind the 16 * ksteps columns of P (overwrites P's zero padding there)
+          if (c2 < 2 * p.ksteps2) {
+            const int c = 2 * p.ksteps + c2;
+            st_shared_v4(prow + (c >> 3) * P_SLAB + ((uint32_t(c & 7) << 4) ^ swz), pk2[c2 * 4], pk2[c2 * 4 + 1], pk2[c2 * 4 + 2], pk2[c2 * 4 + 3]);
+          }
+        }
+      }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncwarp();
@@ -339,17 +403,18 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, int NC>
-int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const ShortParams& prm) {
+template <typename T, int NC, bool DUAL>
+int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
+           const CUtensorMap& mv2, const ShortParams& prm) {
   static PerDeviceOnce configured;
   if (configured.needed()) {
-    if (cudaFuncSetAttribute(tc_sdpa_short_kernel<T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sdpa_short_kernel<T, NC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
       RB200_FAIL(-2, "tc_sdpa_short: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
     configured.done();
   }
   const int64_t cap = sm_count();
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_short_kernel<T, NC><<<grid, THREADS, SMEM_BYTES, st>>>(mq, mk, mv, prm);
+  tc_sdpa_short_kernel<T, NC, DUAL><<<grid, THREADS, SMEM_BYTES, st>>>(mq, mk, mv, mk2, mv2, prm);
   RB200_CHECK_LAUNCH("tc_sdpa_short");
   return 0;
 }
@@ -367,8 +432,13 @@ bool tc_sdpa_short_supported(const SdpaProblem& p) {
   if (!enabled) return false;
   if (p.dtype != RB200_BF16 && p.dtype != RB200_FP16) return false;
   if (p.D < 8 || p.D > 64 || (p.D & 7) != 0 || p.causal) return false;
-  if (p.bias_h != nullptr || (p.k2 != nullptr && p.Sk2 > 0)) return false;
+  if (p.bias_h != nullptr) return false;
   if (p.Sk < 1 || p.Sk > 128 || p.Sq < 1 || p.B < 1) return false;
+  if (p.k2 != nullptr && p.Sk2 > 0) {  // second K / V set: at most 32 keys, and both P tiles must fit the 128 columns of the P buffer
+    static const int dual = env_flag("RB200_ATTN_SHORT_DUAL", 1);
+    if (!dual || p.Sk2 > 32 || p.Sk > 96) return false;  // (16 * ksteps + 16 * ksteps2 <= 128 then holds)
+    if (!ok_operand(p.k2, p.k2_sb, p.k2_ss) || !ok_operand(p.v2, p.v2_sb, p.v2_ss)) return false;
+  }
   if (ceil_div(p.Sq, QT) * p.H * p.B >= (int64_t(1) << 31)) return false;  // 32-bit item arithmetic in the kernel
   return ok_operand(p.q, p.q_sb, p.q_ss) && ok_operand(p.k, p.k_sb, p.k_ss) && ok_operand(p.v, p.v_sb, p.v_ss);
 }
@@ -380,6 +450,13 @@ int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p) {
   if (int rc = make_map(&mk, p.dtype, p.k, p.B, p.Sk, p.H, p.k_sb, p.k_ss, p.D, 16 * ksteps)) return rc;
   if (int rc = make_map(&mv, p.dtype, p.v, p.B, p.Sk, p.H, p.v_sb, p.v_ss, p.D, 16 * ksteps)) return rc;
   const int nc = int(ceil_div(p.Sk, 32));
+  const bool dual = p.k2 != nullptr && p.Sk2 > 0;
+  const int ksteps2 = dual ? int(ceil_div(p.Sk2, 16)) : 0;
+  CUtensorMap mk2 = mk, mv2 = mv;
+  if (dual) {
+    if (int rc = make_map(&mk2, p.dtype, p.k2, p.B, p.Sk2, p.H, p.k2_sb, p.k2_ss, p.D, 16 * ksteps2)) return rc;
+    if (int rc = make_map(&mv2, p.dtype, p.v2, p.B, p.Sk2, p.H, p.v2_sb, p.v2_ss, p.D, 16 * ksteps2)) return rc;
+  }
   ShortParams prm{};
   prm.o = p.o;
   prm.o_sb = p.o_sb;
@@ -391,16 +468,23 @@ int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p) {
   prm.total_work = int64_t(prm.n_qt) * p.H * p.B;
   prm.ksteps = ksteps;
   prm.kv_bytes = 16 * ksteps * 128;
-  prm.stage_bytes = TILE_BYTES + 2 * prm.kv_bytes;
+  prm.Sk2 = dual ? p.Sk2 : 0;
+  prm.ksteps2 = ksteps2;
+  prm.kv2_bytes = 16 * ksteps2 * 128;
+  prm.scale2 = p.scale2;
+  prm.stage_bytes = TILE_BYTES + 2 * prm.kv_bytes + 2 * prm.kv2_bytes;
   prm.nst = RING_BYTES / prm.stage_bytes >= MAX_NST ? MAX_NST : 3;
   prm.scale_log2e = p.scale * 1.4426950408889634f;
   const uint32_t fmt = p.dtype == RB200_BF16 ? 1u : 0u;
   const uint32_t common = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(QT >> 4) << 24);
   prm.idesc_qk = common | (uint32_t((16 * ksteps) >> 3) << 17);      // D = 128 x (16 ksteps): exactly the rows of the K tile
   prm.idesc_pv = common | (uint32_t(HD >> 3) << 17) | (1u << 16);    // D = 128 x 64, B (= V) MN-major
+  prm.idesc_qk2 = common | (uint32_t((16 * (dual ? ksteps2 : 1)) >> 3) << 17);
   prm.d_out = p.D;
   const bool bf = p.dtype == RB200_BF16;
-#define RB200_SHORT(NC) return bf ? launch<__nv_bfloat16, NC>(st, mq, mk, mv, prm) : launch<__half, NC>(st, mq, mk, mv, prm)
+#define RB200_SHORT(NC)                                                                                                      \
+  if (dual) return bf ? launch<__nv_bfloat16, NC, true>(st, mq, mk, mv, mk2, mv2, prm) : launch<__half, NC, true>(st, mq, mk, mv, mk2, mv2, prm); \
+  return bf ? launch<__nv_bfloat16, NC, false>(st, mq, mk, mv, mk2, mv2, prm) : launch<__half, NC, false>(st, mq, mk, mv, mk2, mv2, prm)
   switch (nc) {
     case 1: RB200_SHORT(1);
     case 2: RB200_SHORT(2);

@@ -670,6 +670,31 @@ def test_sdpa_short_keys(cuda_device, dtype, case):
     assert_close(y, ref, dtype, scale=4.0, what=f"short sdpa{case}")
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=str)
+@pytest.mark.parametrize("case", [(8, 20, 1024, 77, 4, 64), (2, 10, 4096, 77, 16, 64), (2, 3, 200, 96, 32, 40), (1, 2, 130, 17, 1, 64), (2, 2, 256, 64, 20, 64)], ids=str)
+def test_sdpa_short_keys_dual_kv(cuda_device, dtype, case):
+    """The IP-Adapter form on the single-pass kernel: both softmaxes share one accumulator (the image tokens' probabilities
+    are pre-scaled by scale2 * l / l2); against fp32 on the same operands, and against the first-generation dual kernel."""
+    import os
+
+    from refiners_b200 import backend as B
+
+    _fp32_reference_mode()
+    Bn, H, Sq, Sk, Sk2, D = case
+    dev = lambda t: t.to(cuda_device, dtype)
+    q, k, v = dev(_gen((Bn, Sq, H * D), 470)), dev(_gen((Bn, Sk, H * D), 471)), dev(_gen((Bn, Sk, H * D), 472))
+    k2, v2 = dev(_gen((Bn, Sk2, H * D), 473) * 2.0), dev(_gen((Bn, Sk2, H * D), 474))
+    with torch.no_grad():
+        y = B.sdpa(q, k, v, H, k2=k2, v2=v2, scale2=0.6)
+        ref = torch.cat([
+            _sdpa_ref(q[i : i + 1].float(), k[i : i + 1].float(), v[i : i + 1].float(), H)
+            + 0.6 * _sdpa_ref(q[i : i + 1].float(), k2[i : i + 1].float(), v2[i : i + 1].float(), H)
+            for i in range(Bn)
+        ])
+        assert torch.equal(y, B.sdpa(q, k, v, H, k2=k2, v2=v2, scale2=0.6))
+    assert_close(y, ref, dtype, scale=4.0, what=f"short dual sdpa{case}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES, ids=str)
 @pytest.mark.parametrize("guided", [True, False], ids=["cfg", "plain"])
 def test_cfg_euler_glue_is_bit_identical_to_the_operator_sequence(cuda_device, dtype, guided):

@@ -65,6 +65,12 @@ elif which in ("attn77", "attn77_4096"):
     q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
     k, v = torch.randn(Bn, 77, H * 64, device=dev, dtype=bf), torch.randn(Bn, 77, H * 64, device=dev, dtype=bf)
     fn, flops = (lambda: B.sdpa(q, k, v, H)), 4.0 * Bn * H * S * 77 * 64
+elif which == "attn77_dual":  # IP-Adapter: text cross-attention + 4 image tokens in one launch
+    Bn, H, S = 16, 20, 1024
+    q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)
+    k, v = torch.randn(Bn, 77, H * 64, device=dev, dtype=bf), torch.randn(Bn, 77, H * 64, device=dev, dtype=bf)
+    k2, v2 = torch.randn(Bn, 4, H * 64, device=dev, dtype=bf), torch.randn(Bn, 4, H * 64, device=dev, dtype=bf)
+    fn, flops = (lambda: B.sdpa(q, k, v, H, k2=k2, v2=v2, scale2=0.6)), 4.0 * Bn * H * S * 81 * 64
 elif which == "attn_sam_win":
     qkv = torch.randn(25, 14, 14, 3 * 1280, device=dev, dtype=bf)
     rh, rw = torch.randn(27, 80, device=dev, dtype=bf), torch.randn(27, 80, device=dev, dtype=bf)
