@@ -181,11 +181,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// LAZY (experimental, RB200_ATTN_LAZY=1; HD = 64, single K/V set, no bias): O accumulates in ONE TMEM buffer across
-// the key tiles (the PV MMAs accumulate) instead of being folded through registers every tile; the softmax keeps a
-// stale running maximum and rescales O in TMEM (tcgen05.ld / st) only when a row's maximum grows by more than 2^8 -
-// FlashAttention-4's conditional rescaling.  Saves the per-tile O read (64 columns) and 128 FP32 ops per thread.
-template <typename T, bool DUAL, int HD, bool BIAS, bool LAZY>
+template <typename T, bool DUAL, int HD, bool BIAS>
 __global__ void __launch_bounds__(NUM_THREADS, Cfg<HD>::CTAS_PER_SM)
 tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
@@ -211,8 +207,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
   uint64_t* bias_full = q_full + 12;     // bias block of this work item landed in sBias
   uint64_t* bias_empty = q_full + 13;    // the four softmax warps are done with it
   float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [(bias_H + bias_W)][128], BIAS only
-  uint64_t* bar_ofree = q_full + 14;     // LAZY: the O accumulator of the finished work item has been read out
-  static_assert(!LAZY || (!DUAL && !BIAS && HD == 64), "lazy rescaling is instantiated for the plain d = 64 case only");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsets = DUAL ? 2 : 1;
@@ -229,7 +223,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     mbar_init(q_empty, 1);
     mbar_init(bias_full, 1);
     mbar_init(bias_empty, 4);
-    if constexpr (LAZY) mbar_init(bar_ofree, 4);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_s[b], 1);
       mbar_init(&bar_sfree[b], 4);
@@ -292,7 +285,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
       int st_s = 0, st_pv = 0;      // ring cursors: stage whose K feeds the next S / whose V feeds the next PV
       uint32_t ph_s = 0, qphase = 0;
       uint32_t g = 0;               // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
-      uint32_t ofree_phase = 0;     // LAZY only
       auto issue_s = [&](uint32_t gt) {
         const uint32_t b = gt & 1, k_use = gt >> 1;
         mbar_wait(&kv_full[st_s], ph_s, 3);
@@ -323,12 +315,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             if (p.early_s && j + 1 < ntiles) issue_s(g + 1);  // S_{j+1} runs while the softmax warps work on S_j
             const uint32_t b = g & 1;
             mbar_wait(&bar_p[b], (g >> 1) & 1, 6);  // P_j in smem buffer b; O buffer b has been drained
-            if constexpr (LAZY) {
-              if (j == 0) {  // the single O accumulator still holds the previous work item until its rows are read out
-                mbar_wait(bar_ofree, ofree_phase ^ 1, 10);
-                ofree_phase ^= 1;
-              }
-            }
             tcgen05_fence_after();
             const uint64_t dp = desc_kmajor(smem_u32(sP + b * P_BYTES));
 #pragma unroll
@@ -337,8 +323,7 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < KT / 16; ++k) {
                 // A: +32 B per 16 keys inside the swizzle atom; B (MN-major): +16 rows * 128 B
-                if constexpr (LAZY) umma_f16(tmem_o + sl * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, (j > 0 || k > 0));
-                else umma_f16(tmem_o + b * HD + sl * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
+                umma_f16(tmem_o + b * HD + sl * 64, dp + uint64_t(k * 2), dv + uint64_t(k * 128), p.idesc_pv, k > 0);
               }
             }
             umma_commit(&kv_empty[st_pv]);  // K_j / V_j slot free once these MMAs retire
@@ -374,104 +359,6 @@ tc_sdpa_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         mbar_wait(bias_full, bias_phase, 9);
         bias_phase ^= 1;
       }
-      if constexpr (LAZY) {
-        // ---- conditional-rescaling variant: O lives in TMEM for the whole work item
-        constexpr float RESCALE_LOG2 = 8.0f;  // tolerate a stale maximum until p could exceed 2^8
-        const int ntiles = int((p.Sk + KT - 1) / KT);
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < ntiles; ++j, ++g) {
-          const uint32_t buf = g & 1;
-          mbar_wait(&bar_s[buf], (g >> 1) & 1, 7);
-          tcgen05_fence_after();
-          float s[KT];
-          {
-            uint32_t raw0[32], raw1[32];
-            tmem_ld_32x32(tmem_s + buf * 64 + lane_off, raw0);
-            tmem_ld_32x32(tmem_s + buf * 64 + lane_off + 32, raw1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              s[i] = __uint_as_float(raw0[i]);
-              s[32 + i] = __uint_as_float(raw1[i]);
-            }
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_relaxed(&bar_sfree[buf]);
-          const int valid = int((p.Sk - int64_t(j) * KT) < KT ? (p.Sk - int64_t(j) * KT) : KT);
-          if (valid < KT) {
-#pragma unroll
-            for (int i = 0; i < KT; ++i)
-              if (i >= valid) s[i] = -INFINITY;
-          }
-          float tmax = s[0];
-#pragma unroll
-          for (int i = 1; i < KT; ++i) tmax = fmaxf(tmax, s[i]);
-          const float m_new = fmaxf(m_run, tmax);
-          if (j == 0) {
-            m_run = m_new;  // nothing accumulated yet
-          } else {
-            const bool grew = (m_new - m_run) * p.scale_log2e > RESCALE_LOG2;
-            if (__any_sync(0xffffffffu, grew)) {  // TMEM access is warp-collective: the whole warp rescales its 32 rows
-              const uint32_t gp = g - 1;
-              mbar_wait(&bar_o[gp & 1], (gp >> 1) & 1, 8);  // every PV issued so far has landed in O
-              tcgen05_fence_after();
-              const float alpha = fast_exp2((m_run - m_new) * p.scale_log2e);
-#pragma unroll
-              for (int half = 0; half < HD / 32; ++half) {
-                uint32_t raw[32];
-                tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
-                tmem_st_32x32(tmem_o + lane_off + half * 32, raw);
-              }
-              tmem_st_wait();
-              l_run *= alpha;
-              m_run = m_new;
-            }
-          }
-          const float mb = m_run * p.scale_log2e;
-          float psum = 0.f;
-          uint32_t packed[KT / 2];
-#pragma unroll
-          for (int i = 0; i < KT; i += 2) {
-            const float p0 = fast_exp2(fmaf(s[i], p.scale_log2e, -mb));
-            const float p1 = fast_exp2(fmaf(s[i + 1], p.scale_log2e, -mb));
-            psum += p0 + p1;
-            packed[i / 2] = pack2<T>(p0, p1);
-          }
-          l_run += psum;
-          // P buffer `buf` was last read by PV_{g-2}
-          if (g >= 2) mbar_wait(&bar_o[buf], ((g - 2) >> 1) & 1, 11);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 v = make_uint4(packed[c * 4], packed[c * 4 + 1], packed[c * 4 + 2], packed[c * 4 + 3]);
-            *reinterpret_cast<uint4*>(prow + buf * P_BYTES + ((c ^ sw) << 4)) = v;
-          }
-          fence_proxy_async();
-          tcgen05_fence_before();  // also orders a rescale's tcgen05.st before the MMA that the arrive releases
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_p[buf]);
-        }
-        {
-          const uint32_t gp = g - 1;
-          mbar_wait(&bar_o[gp & 1], (gp >> 1) & 1, 9);
-          tcgen05_fence_after();
-          const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-#pragma unroll
-          for (int half = 0; half < HD / 32; ++half) {
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_o + lane_off + half * 32, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) acc[half * 32 + i] = inv * __uint_as_float(raw[i]);
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_relaxed(bar_ofree);  // the MMA warp may start the next work item's PV
-        }
-      } else
       for (int set = 0; set < nsets; ++set) {
         const int64_t Sk = set ? p.Sk2 : p.Sk;
         const int ntiles = int((Sk + KT - 1) / KT);
@@ -677,20 +564,20 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, bool DUAL, int HD, bool BIAS, bool LAZY = false>
+template <typename T, bool DUAL, int HD, bool BIAS>
 int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
            const CUtensorMap& mv2, const AttnParams& prm) {
   static PerDeviceOnce configured;
   constexpr size_t SMEM_MAX = Cfg<HD>::SMEM_BYTES + (BIAS ? MAX_BIAS_BYTES : 0);
   const size_t SMEM = Cfg<HD>::SMEM_BYTES + (BIAS ? prm.bias_bytes : 0);
   if (configured.needed()) {
-    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS, LAZY>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_MAX)) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sdpa_kernel<T, DUAL, HD, BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_MAX)) != cudaSuccess)
       RB200_FAIL(-2, "tc_sdpa: cannot reserve %zu bytes of shared memory", SMEM_MAX);
     configured.done();
   }
   const int64_t cap = int64_t(sm_count()) * Cfg<HD>::CTAS_PER_SM;
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_kernel<T, DUAL, HD, BIAS, LAZY><<<grid, NUM_THREADS, SMEM, st>>>(mq, mk, mv, mk2, mv2, prm);
+  tc_sdpa_kernel<T, DUAL, HD, BIAS><<<grid, NUM_THREADS, SMEM, st>>>(mq, mk, mv, mk2, mv2, prm);
   RB200_CHECK_LAUNCH("tc_sdpa");
   return 0;
 }
@@ -701,11 +588,6 @@ int dispatch(cudaStream_t st, const SdpaProblem& p, bool dual, const CUtensorMap
   const bool bias = p.bias_h != nullptr;
   if (p.D <= 64) {
     if (bias) RB200_FAIL(-1, "tc_sdpa: bias with head dim 64 is not instantiated");
-    static const bool lazy = [] {
-      const char* e = getenv("RB200_ATTN_LAZY");  // experimental conditional-rescaling variant, off by default
-      return e && atoi(e) != 0;
-    }();
-    if (!dual && lazy) return launch<T, false, 64, false, true>(st, mq, mk, mv, mk2, mv2, prm);
     return dual ? launch<T, true, 64, false>(st, mq, mk, mv, mk2, mv2, prm) : launch<T, false, 64, false>(st, mq, mk, mv, mk2, mv2, prm);
   }
   if (dual) RB200_FAIL(-1, "tc_sdpa: dual K/V with head dim 128 is not instantiated");
