@@ -62,9 +62,15 @@ def _stamp_of(t: Tensor) -> tuple[int, int, tuple[int, ...]]:
     return (t.data_ptr(), t._version, tuple(t.shape))
 
 
-def _signature(v: Any) -> Any:
+def _signature(v: Any, nested: bool = False) -> Any:
+    """What a capture depends on in a context value.  A tensor stored directly is mirrored in a static buffer (any tensor of
+    that shape and dtype can be copied in); tensors INSIDE a container (the tuple of T2I-Adapter feature maps, a list of
+    residuals) are used by the captured kernels at their own addresses, so they count by identity and version; everything
+    else by ``repr``."""
     if isinstance(v, Tensor):
-        return ("tensor", tuple(v.shape), v.dtype)
+        return ("tensor", tuple(v.shape), v.dtype, *(_stamp_of(v) if nested else ()))
+    if isinstance(v, (tuple, list)):
+        return (type(v).__name__, tuple(_signature(item, nested=True) for item in v))
     return ("value", repr(v))
 
 

@@ -31,6 +31,7 @@ _PLAIN = (float, int, bool, str, list, tuple)
 # module.  Such values end up as kernel arguments and inside packed weights; a captured CUDA graph
 # (refiners_b200.engine.graph) compares this counter to know that its baked-in copies are stale.
 _value_epoch = 0
+_UNSET = object()
 
 
 def value_epoch() -> int:
@@ -53,8 +54,10 @@ class Module(torch.nn.Module):
 
     def __setattr__(self, name: str, value: Any) -> None:
         if isinstance(value, _PLAIN) and name[:1] != "_":
-            global _value_epoch
-            _value_epoch += 1
+            held = self.__dict__.get(name, _UNSET)
+            if type(held) is not type(value) or held != value:  # re-assigning the value already held changes nothing
+                global _value_epoch
+                _value_epoch += 1
         super().__setattr__(name, value)
 
     def load_from_safetensors(self: T, tensors_path: str | Path, strict: bool = True) -> T:

@@ -249,3 +249,24 @@ def test_sdpa_module_matches_reference_formula_and_slicing():
         plain = fl.ScaledDotProductAttention(num_heads=4, is_optimized=False)(q, k, v)
         sliced = fl.ScaledDotProductAttention(num_heads=4, slice_size=3)(q, k, v)
     assert torch.allclose(full, plain, atol=1e-6) and torch.allclose(full, sliced, atol=1e-6)
+
+
+def test_value_epoch_counts_real_changes_only():
+    """The CUDA-graph runner re-captures when a public scalar of any module changes (engine/graph.py): re-assigning the value a
+    module already holds - a pipeline that sets ``adapter.scale = s`` on every step - must not count."""
+    import refiners_b200.fluxion.layers as fl
+    from refiners_b200.fluxion.layers.base import value_epoch
+
+    m = fl.Multiply(scale=0.5)
+    start = value_epoch()
+    m.scale = 0.5
+    assert value_epoch() == start
+    m.scale = 0.25
+    assert value_epoch() == start + 1
+    m.scale = 0.25
+    m._private = 3
+    assert value_epoch() == start + 1
+    m.scale = 1  # an int is not the float 1.0 held before? it is a different value here anyway
+    assert value_epoch() == start + 2
+    m.scale = 1.0  # same number, different type: counts (kernels may specialise on it)
+    assert value_epoch() == start + 3

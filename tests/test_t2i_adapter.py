@@ -102,3 +102,39 @@ def test_avg_pool_kernel(cuda_device, dtype):
         assert got.shape == want.shape
         eps = {torch.float32: 1e-6, torch.bfloat16: 2**-8, torch.float16: 2**-11}[dtype]
         assert (got.float() - want).abs().max().item() <= eps * want.abs().max().item() + 1e-7
+
+
+@pytest.mark.gpu
+def test_t2i_adapter_under_cuda_graph(cuda_device):
+    """The feature maps reach the UNet as a TUPLE of tensors in a context: the captured graph reads them at their own
+    addresses, so a replay must follow new features (identity-based signature -> re-capture), a new scale (value epoch),
+    and otherwise replay without re-capturing."""
+    from refiners_b200.engine.graph import GraphedChain
+
+    dtype = torch.bfloat16
+    unet = SD1UNet(4, device="meta")
+    keyed(unet, 1, cuda_device, dtype)
+    adapter = SD1T2IAdapter(unet, name="depth", scale=0.8)
+    keyed(adapter.condition_encoder, 31, cuda_device, dtype)
+    adapter.inject()
+    x = keyed_input("t2i.sd1.x", (1, 4, 32, 32)).to(cuda_device, dtype)
+    ctx = keyed_input("t2i.sd1.ctx", (1, 77, 768)).to(cuda_device, dtype)
+    timestep = torch.tensor([601.0], device=cuda_device)
+
+    def contexts(features):
+        unet.set_timestep(timestep)
+        unet.set_clip_text_embedding(ctx)
+        adapter.set_condition_features(features)
+
+    with no_grad():
+        f1 = adapter.compute_condition_features(keyed_input("t2i.sd1.condition", (1, 3, 256, 256)).to(cuda_device, dtype))
+        f2 = tuple(f * 0.5 for f in f1)
+        runner = GraphedChain(unet)
+        for features, scale in ((f1, 0.8), (f1, 0.8), (f2, 0.8), (f2, 0.3), (f1, 0.3)):
+            adapter.scale = scale
+            contexts(features)
+            want = unet(x)
+            contexts(features)
+            got = runner(x).clone()
+            assert torch.equal(got, want), (scale, features is f1)
+        assert runner.captures == 4 and runner.replays == 5  # the second call replays, every change re-captures
