@@ -55,6 +55,11 @@ class Module(torch.nn.Module):
     def __setattr__(self, name: str, value: Any) -> None:
         if isinstance(value, _PLAIN) and name[:1] != "_":
             held = self.__dict__.get(name, _UNSET)
+            if held is _UNSET and isinstance(getattr(type(self), name, None), property):
+                try:  # a property (adapter.scale forwarding to its layers): compare with what it reads now
+                    held = getattr(self, name)
+                except Exception:
+                    held = _UNSET
             if type(held) is not type(value) or held != value:  # re-assigning the value already held changes nothing
                 global _value_epoch
                 _value_epoch += 1

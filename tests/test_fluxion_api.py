@@ -270,3 +270,19 @@ def test_value_epoch_counts_real_changes_only():
     assert value_epoch() == start + 2
     m.scale = 1.0  # same number, different type: counts (kernels may specialise on it)
     assert value_epoch() == start + 3
+
+    class Forwarding(fl.Chain):  # an adapter-style property that forwards to a child
+        @property
+        def scale(self) -> float:
+            return self[0].scale
+
+        @scale.setter
+        def scale(self, value: float) -> None:
+            self[0].scale = value
+
+    f = Forwarding(fl.Multiply(scale=2.0))
+    start = value_epoch()
+    f.scale = 2.0
+    assert value_epoch() == start
+    f.scale = 3.0
+    assert value_epoch() == start + 2 and f[0].scale == 3.0  # the property assignment and the child's attribute
