@@ -44,9 +44,7 @@ constexpr int RING_BYTES = 144 * 1024;          // stages of {Q | K | V}: 4 x 36
 constexpr int P_SLAB = QT * 64 * 2;             // 64 keys of P for 128 rows
 constexpr int P_BYTES = 2 * P_SLAB;
 constexpr int TMEM_COLS = 512;
-constexpr int XCHG_BYTES = 2 /*max, sum*/ * 2 /*groups*/ * 2 /*halves*/ * QT * 4;   // row maxima / sums exchanged between column halves
-constexpr size_t SMEM_BYTES = RING_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/ + XCHG_BYTES;
-constexpr int THREADS_SPLIT = 640;  // warps 0-3: TMA, MMA, two idle (a warpgroup for setmaxnreg); 16 softmax warps
+constexpr size_t SMEM_BYTES = RING_BYTES + 2 * P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(SMEM_BYTES <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
 
 struct ShortParams {
@@ -81,11 +79,11 @@ template <> __device__ __forceinline__ uint32_t pack2s<__half>(float a, float b)
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// NC = 32-column chunks of logits per row (Sk <= 32 * NC).  SPLIT = false: one thread per query row (8 softmax warps);
-// SPLIT = true: TWO threads per row, each owning 16 * NC columns (16 softmax warps, row maximum and sum exchanged through
-// shared memory and a named barrier): half the dependent work per warp and twice the warps per scheduler.
-template <typename T, int NC, bool DUAL, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? THREADS_SPLIT : THREADS, 1)
+// NC = 32-column chunks of logits per row (Sk <= 32 * NC).  One thread per query row: a variant with two threads per row (16
+// softmax warps, row maximum and sum exchanged through shared memory and a named barrier) measured SLOWER - 38.9 vs 32.8 us at
+// Sq = 1024, 69.6 vs 53.2 us at Sq = 4096 (session V): the two exchanges per item cost more than the extra warps hide.
+template <typename T, int NC, bool DUAL>
+__global__ void __launch_bounds__(THREADS, 1)
 tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_k2,
                      const __grid_constant__ CUtensorMap map_v2, const ShortParams p) {
@@ -102,9 +100,6 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* bar_o = bar_s + 6;         // [2] O_g is in TMEM
   uint64_t* bar_ofree = bar_s + 8;     // [2] group g has read O_g out
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_s + 10);
-  float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [max | sum][group][half][row]
-  constexpr int FIRST = SPLIT ? 4 : 2;       // first softmax warp
-  constexpr uint32_t ARRIVALS = SPLIT ? 8 : 4;  // softmax warps per group
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -118,10 +113,10 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar_s[g], 1);
-      mbar_init(&bar_sfree[g], ARRIVALS);
-      mbar_init(&bar_p[g], ARRIVALS);
+      mbar_init(&bar_sfree[g], 4);
+      mbar_init(&bar_p[g], 4);
       mbar_init(&bar_o[g], 1);
-      mbar_init(&bar_ofree[g], ARRIVALS);
+      mbar_init(&bar_ofree[g], 4);
     }
     fence_barrier_init();
   }
@@ -219,191 +214,9 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
     }
   };
-  if constexpr (SPLIT) {
-    // the register budgets are set inside the role branches: ptxas sizes each region by the setmaxnreg that dominates it
-    if (warp < FIRST) {
-      setmaxnreg_dec<40>();
-      if (warp == 0) producer();
-      else if (warp == 1) issuer();
-    } else {
-      setmaxnreg_inc<112>();
-    // ================================================================== softmax + epilogue, two threads per query row
-    {
-      constexpr int NH = NC;                 // 16-column chunks per thread
-      const int sw_i = warp - FIRST;
-      const int g = sw_i >> 3;               // group: items of parity g
-      const int hf = (sw_i >> 2) & 1;        // column half of the row (and 32 output columns)
-      const int lg = warp & 3;
-      const int row = lg * 32 + lane;
-      const uint32_t lane_off = uint32_t(lg * 32) << 16;
-      const int col0 = hf * 16 * NH;
-      const uint32_t tmem_s = tmem_base + g * 128 + col0 + lane_off;
-      const uint32_t tmem_o = tmem_base + 256 + g * 64 + hf * 32 + lane_off;
-      const uint32_t prow = smem_u32(sP + g * P_BYTES + row * 128);
-      const uint32_t swz = uint32_t(row & 7) << 4;
-      const uint32_t a_s = smem_u32(&bar_s[g]), a_sfree = smem_u32(&bar_sfree[g]), a_p = smem_u32(&bar_p[g]);
-      const uint32_t a_o = smem_u32(&bar_o[g]), a_ofree = smem_u32(&bar_ofree[g]);
-      const uint32_t xm = smem_u32(xchg + (g * 2) * QT), xs = smem_u32(xchg + (4 + g * 2) * QT);
-      const uint32_t xm_mine = xm + uint32_t(hf * QT + row) * 4, xm_other = xm + uint32_t((hf ^ 1) * QT + row) * 4;
-      const uint32_t xs_mine = xs + uint32_t(hf * QT + row) * 4, xs_other = xs + uint32_t((hf ^ 1) * QT + row) * 4;
-      const uint32_t xbar = 1 + g;           // named barrier of the group's 256 threads
-      T* obase = static_cast<T*>(p.o);
-      const int left0 = int(p.Sk) - col0;    // valid keys among this thread's columns (may be <= 0 or >= 16 NH)
-      struct Pending { T* dst; float inv; bool live; };
-      Pending pending{nullptr, 0.f, false};
-      auto flush = [&](uint32_t k_done) {    // this thread's 32 output columns of the group's item k_done
-        mbar_wait_a(a_o, k_done & 1);
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_o, r);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed_a(a_ofree);
-        if (!pending.live) return;
-        T* dst = pending.dst;
-        const float inv = pending.inv;
-        const int first = hf * 32;
-        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (p.d_out & 7) == 0) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (first + c * 8 >= p.d_out) break;
-            uint4 v;
-            v.x = pack2s<T>(inv * __uint_as_float(r[c * 8]), inv * __uint_as_float(r[c * 8 + 1]));
-            v.y = pack2s<T>(inv * __uint_as_float(r[c * 8 + 2]), inv * __uint_as_float(r[c * 8 + 3]));
-            v.z = pack2s<T>(inv * __uint_as_float(r[c * 8 + 4]), inv * __uint_as_float(r[c * 8 + 5]));
-            v.w = pack2s<T>(inv * __uint_as_float(r[c * 8 + 6]), inv * __uint_as_float(r[c * 8 + 7]));
-            reinterpret_cast<uint4*>(dst)[c] = v;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (first + e < p.d_out) dst[e] = from_f<T>(inv * __uint_as_float(r[e]));
-        }
-      };
-      uint32_t k = 0;
-      for (uint32_t i = g; i < n_items; i += 2, ++k) {
-        const uint32_t w = blockIdx.x + i * gridDim.x;
-        const int qt = int(w % n_qt), h = int((w / n_qt) % heads);
-        const int64_t b = w / (n_qt * heads);
-        mbar_wait_a(a_s, k & 1);
-        tcgen05_fence_after();
-        float s[NH * 16];
-        float s2[DUAL ? 32 : 1];
-        {
-          uint32_t raw[NH][16];
-#pragma unroll
-          for (int c = 0; c < NH; ++c) tmem_ld_32x16(tmem_s + c * 16, raw[c]);
-          if constexpr (DUAL) {
-            if (hf == 0) {  // (warp-uniform) the image tokens' logits go with the first half
-              uint32_t raw2[32];
-              tmem_ld_32x32(tmem_base + 384 + g * 32 + lane_off, raw2);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 32; ++e) s2[e] = __uint_as_float(raw2[e]);
-            }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < NH; ++c)
-#pragma unroll
-            for (int e = 0; e < 16; ++e) s[c * 16 + e] = __uint_as_float(raw[c][e]);
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed_a(a_sfree);
-        if (left0 < NH * 16) {
-#pragma unroll
-          for (int e = 0; e < NH * 16; ++e)
-            if (e >= left0) s[e] = -INFINITY;
-        }
-        float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
-#pragma unroll
-        for (int e = 4; e < NH * 16; e += 4) {
-          m0 = fmaxf(m0, s[e]);
-          m1 = fmaxf(m1, s[e + 1]);
-          m2 = fmaxf(m2, s[e + 2]);
-          m3 = fmaxf(m3, s[e + 3]);
-        }
-        const float mine = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        st_shared_f32(xm_mine, mine);
-        named_bar_sync(xbar, 256);
-        const float mb = fmaxf(mine, ld_shared_f32(xm_other)) * p.scale_log2e;  // (half 0 holds >= 1 valid key: finite)
-        const uint64_t sc2 = f32x2(p.scale_log2e, p.scale_log2e), nmb2 = f32x2(-mb, -mb);
-        uint64_t sum_a = f32x2(0.f, 0.f), sum_b = sum_a;
-        uint32_t pk[NH * 8];
-#pragma unroll
-        for (int e = 0; e < NH * 16; e += 4) {
-          float x0, x1, x2, x3;
-          f32x2_split(fma_f32x2(f32x2(s[e], s[e + 1]), sc2, nmb2), x0, x1);
-          f32x2_split(fma_f32x2(f32x2(s[e + 2], s[e + 3]), sc2, nmb2), x2, x3);
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1), p2 = ex2_approx(x2), p3 = ex2_approx(x3);
-          sum_a = add_f32x2(sum_a, f32x2(p0, p1));
-          sum_b = add_f32x2(sum_b, f32x2(p2, p3));
-          pk[e / 2] = pack2s<T>(p0, p1);
-          pk[e / 2 + 1] = pack2s<T>(p2, p3);
-        }
-        float l0, l1;
-        f32x2_split(add_f32x2(sum_a, sum_b), l0, l1);
-        st_shared_f32(xs_mine, l0 + l1);
-        named_bar_sync(xbar, 256);   // (also: both halves have read the maxima before the next item overwrites them)
-        const float l = l0 + l1 + ld_shared_f32(xs_other);
-        uint32_t pk2[DUAL ? 16 : 1];
-        if constexpr (DUAL) {
-          if (hf == 0) {
-            const int sk2 = int(p.Sk2);
-            float mm = -INFINITY;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              if (e >= sk2) s2[e] = -INFINITY;
-              mm = fmaxf(mm, s2[e]);
-            }
-            const float mb2 = mm * p.scale_log2e;
-            float l2 = 0.f;
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              s2[e] = ex2_approx(fmaf(s2[e], p.scale_log2e, -mb2));
-              l2 += s2[e];
-            }
-            const float f = p.scale2 * l / l2;
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) pk2[e / 2] = pack2s<T>(s2[e] * f, s2[e + 1] * f);
-          }
-        }
-        if (k > 0) flush(k - 1);
-#pragma unroll
-        for (int j = 0; j < NH * 2; ++j) {  // 16-byte chunks of 8 keys; columns >= 16 * ksteps belong to nobody (or to P2')
-          const int c = hf * 2 * NH + j;
-          if (c < 2 * p.ksteps)
-            st_shared_v4(prow + (c >> 3) * P_SLAB + ((uint32_t(c & 7) << 4) ^ swz), pk[j * 4], pk[j * 4 + 1], pk[j * 4 + 2], pk[j * 4 + 3]);
-        }
-        if constexpr (DUAL) {
-          if (hf == 0) {
-#pragma unroll
-            for (int c2 = 0; c2 < 4; ++c2) {
-              if (c2 < 2 * p.ksteps2) {
-                const int c = 2 * p.ksteps + c2;
-                st_shared_v4(prow + (c >> 3) * P_SLAB + ((uint32_t(c & 7) << 4) ^ swz), pk2[c2 * 4], pk2[c2 * 4 + 1], pk2[c2 * 4 + 2], pk2[c2 * 4 + 3]);
-              }
-            }
-          }
-        }
-        fence_proxy_async();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_a(a_p);
-        const int64_t qi = int64_t(qt) * QT + row;
-        pending.live = qi < p.Sq;
-        pending.dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out + hf * 32;
-        pending.inv = 1.0f / l;
-      }
-      if (k > 0) flush(k - 1);
-    }
-    }
-  } else {
-    if (warp == 0) producer();
-    else if (warp == 1) issuer();
-    else {
+  if (warp == 0) producer();
+  else if (warp == 1) issuer();
+  else {
     // ==================================================================================== softmax + epilogue
     const int g = (warp - 2) >> 2;        // group: items of parity g
     const int lg = warp & 3;              // TMEM lane group this warp may access
@@ -558,7 +371,6 @@ tc_sdpa_short_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       pending.inv = 1.0f / (l0 + l1);
     }
     if (k > 0) flush(k - 1);
-      }
   }
 
   tcgen05_fence_before();
@@ -603,18 +415,18 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, int NC, bool DUAL, bool SPLIT>
+template <typename T, int NC, bool DUAL>
 int launch(cudaStream_t st, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mk2,
            const CUtensorMap& mv2, const ShortParams& prm) {
   static PerDeviceOnce configured;
   if (configured.needed()) {
-    if (cudaFuncSetAttribute(tc_sdpa_short_kernel<T, NC, DUAL, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sdpa_short_kernel<T, NC, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
       RB200_FAIL(-2, "tc_sdpa_short: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
     configured.done();
   }
   const int64_t cap = sm_count();
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_short_kernel<T, NC, DUAL, SPLIT><<<grid, SPLIT ? THREADS_SPLIT : THREADS, SMEM_BYTES, st>>>(mq, mk, mv, mk2, mv2, prm);
+  tc_sdpa_short_kernel<T, NC, DUAL><<<grid, THREADS, SMEM_BYTES, st>>>(mq, mk, mv, mk2, mv2, prm);
   RB200_CHECK_LAUNCH("tc_sdpa_short");
   return 0;
 }
@@ -682,24 +494,15 @@ int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_qk2 = common | (uint32_t((16 * (dual ? ksteps2 : 1)) >> 3) << 17);
   prm.d_out = p.D;
   const bool bf = p.dtype == RB200_BF16;
-  // RB200_ATTN_SHORT_SPLIT: 1 (default) = two threads per query row (16 softmax warps), 0 = one thread per row (8 warps)
-  static const int split = env_flag("RB200_ATTN_SHORT_SPLIT", 1);
-#define RB200_SHORT_AS(NC, DUAL, SPLIT)                                                           \
-  return bf ? launch<__nv_bfloat16, NC, DUAL, SPLIT>(st, mq, mk, mv, mk2, mv2, prm) : launch<__half, NC, DUAL, SPLIT>(st, mq, mk, mv, mk2, mv2, prm)
-#define RB200_SHORT(NC)                     \
-  if (split) {                              \
-    if (dual) { RB200_SHORT_AS(NC, true, true); }   \
-    RB200_SHORT_AS(NC, false, true);        \
-  }                                         \
-  if (dual) { RB200_SHORT_AS(NC, true, false); }    \
-  RB200_SHORT_AS(NC, false, false)
+#define RB200_SHORT(NC)                                                                                                      \
+  if (dual) return bf ? launch<__nv_bfloat16, NC, true>(st, mq, mk, mv, mk2, mv2, prm) : launch<__half, NC, true>(st, mq, mk, mv, mk2, mv2, prm); \
+  return bf ? launch<__nv_bfloat16, NC, false>(st, mq, mk, mv, mk2, mv2, prm) : launch<__half, NC, false>(st, mq, mk, mv, mk2, mv2, prm)
   switch (nc) {
     case 1: RB200_SHORT(1);
     case 2: RB200_SHORT(2);
     case 3: RB200_SHORT(3);
     default: RB200_SHORT(4);
   }
-#undef RB200_SHORT_AS
 #undef RB200_SHORT
 }
 

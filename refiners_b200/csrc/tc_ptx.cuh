@@ -217,6 +217,11 @@ static __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// setmaxnreg moves registers between the warpgroups of ONE CTA: the pool is what the CTA was launched with (threads x the
+// kernel's register count - ptxas sizes that from __launch_bounds__), not the SM's 64 K.  An .inc that the .dec's of the other
+// warpgroups cannot pay for blocks forever (measured the hard way: 640 threads x 96 registers = 61440; 128 x 40 + 512 x 112 does
+// not fit, 128 x 32 + 512 x 112 does).  ptxas allocates each region for the setmaxnreg that DOMINATES it: issue it at the top of
+// the role branch, not in a preamble whose control flow merges again.
 template <int N>
 static __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
