@@ -17,6 +17,7 @@ import torch
 from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
+from refiners_b200 import backend as B
 from refiners_b200.fluxion.context import Contexts
 
 Device = torch.device
@@ -47,6 +48,8 @@ class PerceiverScaledDotProductAttention(fl.Module):
     def forward(self, key_value: Tensor, query: Tensor) -> Tensor:
         batch, length, _ = query.shape
         key, value = key_value.chunk(2, dim=-1)
+        if query.is_cuda:  # (q d^-1/4) (k d^-1/4)^T = q k^T d^-1/2: the library's attention (fp32 softmax inside), strided k / v read in place
+            return B.sdpa(query, key, value, self.num_heads)
         q, k, v = self.reshape_tensor(query), self.reshape_tensor(key), self.reshape_tensor(value)
         logits = (q * self.scale) @ (k * self.scale).transpose(-2, -1)
         weights = torch.softmax(input=logits.float(), dim=-1).type(logits.dtype)

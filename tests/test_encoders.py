@@ -239,3 +239,21 @@ def test_sdxl_double_text_encoder_gpu(cuda_device, dtype):
     tol = 2e-4 if dtype == torch.float32 else 4e-2
     print(f"\n[DoubleTextEncoder {dtype}] embedding max-abs {e1:.3e}, pooled {e2:.3e} of max|ref|")
     assert e1 <= tol and e2 <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=str)
+def test_perceiver_resampler_gpu(cuda_device, dtype):
+    """IP-Adapter "plus": the PerceiverResampler (CLIP patch features -> 16 prompt tokens) on the kernels against its own host
+    evaluation in fp32 (which tests/test_reference_structure.py holds bit-identical to the reference's)."""
+    from refiners_b200.foundationals.latent_diffusion.perceiver import PerceiverResampler
+
+    torch.manual_seed(4)
+    model = PerceiverResampler(latents_dim=128, num_attention_layers=2, num_attention_heads=2, head_dim=64, num_tokens=16,
+                               input_dim=96, output_dim=80)
+    x = torch.randn(2, 257, 96)
+    with no_grad():
+        want = model(x)
+        got = model.to(cuda_device, dtype)(x.to(cuda_device, dtype))
+    e_max, _ = rel_err(got, want)
+    assert e_max <= (2e-4 if dtype == torch.float32 else 3e-2), e_max
