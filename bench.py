@@ -294,6 +294,66 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_config1(args) -> None:
+    """BASELINE config 1: SD1UNet single forward, 64x64 latent, batch 1, fp32 on the CPU - plumbing and correctness, no GPU.
+    The host path of this package (leaves fall through to their torch.nn parents) is timed against the oracle port calling
+    the reference's own ATen ops, on the same inputs and weights, and the two outputs are compared."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import ops as oops
+    from oracle import unet as ounet
+    from oracle.weights import keyed_state_dict
+    from refiners_b200.fluxion.utils import manual_seed, no_grad
+    from refiners_b200.foundationals.latent_diffusion import SD1UNet
+
+    threads = usable_cores()
+    torch.set_num_threads(threads)
+    manual_seed(0)
+    unet = SD1UNet(in_channels=4, device="meta")
+    sd = keyed_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=1)
+    unet.load_state_dict(sd, assign=True)
+    x, ctx, ts = torch.randn(1, 4, 64, 64), torch.randn(1, 77, 768), torch.tensor([[500.0]])
+
+    def engine() -> torch.Tensor:
+        unet.set_timestep(ts)
+        unet.set_clip_text_embedding(ctx)
+        return unet(x)
+
+    def reference() -> torch.Tensor:
+        return ounet.sd1_unet(sd, x, ts, ctx)
+
+    prev, oops.FAST = oops.FAST, True
+    try:
+        with no_grad():
+            repeats = max(5, min(args.steps, 10))
+            times = {}
+            for name, fn in (("engine", engine), ("reference", reference)):
+                for _ in range(max(args.warmup, 1)):
+                    out = fn()
+                t0 = time.perf_counter()
+                for _ in range(repeats):
+                    out = fn()
+                times[name] = ((time.perf_counter() - t0) / repeats, out)
+    finally:
+        oops.FAST = prev
+    (t_engine, y), (t_ref, y_ref) = times["engine"], times["reference"]
+    err = float((y - y_ref).abs().max() / y_ref.abs().max())
+    if not err <= 1e-5:
+        raise SystemExit(f"bench.py --config 1: host path differs from the reference's ATen evaluation by {err:.3e}")
+    line = {
+        "metric": "SD1UNet 64x64 fp32 forwards/s on the CPU (BASELINE config 1: plumbing, no GPU)", "value": 1.0 / t_engine,
+        "unit": "forwards/s", "n_gpus": 0, "steps": repeats, "warmup": max(args.warmup, 1), "ms_per_step": t_engine * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SD1UNet(in_channels=4) fp32, x 1x4x64x64, text 1x77x768, timestep 500, one forward on the host",
+                   "baseline_config": 1, "max_rel_diff_vs_reference_ops": err, "threads": threads},
+        "gpu_launches": 0,
+        "cpu_baseline": {"value": 1.0 / t_ref, "unit": "forwards/s", "cores": threads, "kind": "port",
+                         "sample": f"{repeats} full forwards of the same workload through the oracle port (the reference's ATen CPU ops)"},
+        "e2e": {"value": 1.0 / t_engine, "unit": "forwards/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def workload_name(cfg: int, lb: int) -> str:
     if cfg == 5:
         return f"SAMViTH image encoder, {lb} x 3 x 1024 x 1024 per GPU, bf16"
@@ -682,7 +742,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[] index + 1")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[] index + 1 (1 = the CPU plumbing case)")
     ap.add_argument("--latent-batch", type=int, default=None, help="latents (config 5: images) per GPU; default per config")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -691,6 +751,9 @@ def main() -> None:
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    if args.config == 1:
+        run_config1(args)
+        return
     if args.latent_batch is None:
         args.latent_batch = LATENT_BATCH[args.config]
     if args.impl == "reference":
