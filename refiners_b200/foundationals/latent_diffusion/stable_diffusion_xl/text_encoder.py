@@ -1,19 +1,17 @@
 """SDXL's two text towers as one module: prompt -> ([B, 77, 768 + 1280] token embedding, [B, 1280] pooled embedding).
 
-Contract (class names, trees, context name, call results) from
-/root/reference/src/refiners/foundationals/latent_diffusion/stable_diffusion_xl/text_encoder.py: `TextEncoderWithPooling`
-:13-62, `DoubleTextEncoder` :65-101.
+Class names, trees (= checkpoint keys), the context name and the call results are the contract of
+/root/reference/src/refiners/foundationals/latent_diffusion/stable_diffusion_xl/text_encoder.py (`TextEncoderWithPooling`
+:13-62, `DoubleTextEncoder` :65-101).
 
-Both towers are read at their PENULTIMATE layer (the chain minus its last transformer layer and final LayerNorm).  The
-bigG tower additionally produces the pooled embedding SDXL feeds to its timestep embedding: the remaining layer and the
-final norm are run on a side branch, projected (bias-free 1280 x 1280 Linear) and read at each prompt's end-of-text
-position, which a probe behind the tokenizer records.  `TextEncoderWithPooling` is an ADAPTER around the bigG tower, so
-that the tower keeps its plain tree (and checkpoint keys) when ejected.
+Both towers are read at their PENULTIMATE layer: the chain without its last transformer layer and final LayerNorm.  The bigG
+tower also yields the pooled embedding SDXL feeds to its timestep embedding: a side branch runs the remaining layer and the
+final norm, projects (bias-free 1280 x 1280 Linear) and reads each prompt at its end-of-text token, whose position a probe
+behind the tokenizer has noted.  `TextEncoderWithPooling` is an ADAPTER around the bigG tower, so the tower keeps its plain
+tree and keys when the adapter is ejected.
 """
 
 from __future__ import annotations
-
-from typing import cast
 
 import torch
 from torch import Tensor
@@ -27,26 +25,28 @@ from refiners_b200.foundationals.clip.tokenizer import CLIPTokenizer
 Device = torch.device
 DType = torch.dtype
 
-POOLING = "text_encoder_pooling"
+_POOLING = "text_encoder_pooling"     # context
+_POSITIONS = "end_of_text_index"      # its key: one position per prompt of the batch, appended in order
+_TAIL = 2                             # modules cut off a tower to read it at the penultimate layer: last layer + final norm
+
+
+def first_end_of_text(tokens: Tensor, end_of_text_token_id: int) -> list[int]:
+    """Column of the first end-of-text token in every row (argmax returns the first maximum)."""
+    return (tokens == end_of_text_token_id).to(torch.uint8).argmax(dim=1).tolist()
 
 
 class TextEncoderWithPooling(fl.Chain, Adapter[CLIPTextEncoderG]):
     def __init__(self, target: CLIPTextEncoderG, projection: fl.Linear | None = None) -> None:
         with self.setup_adapter(target=target):
-            head = fl.Chain(
-                target[-2:],  # last transformer layer + final LayerNorm
-                projection or fl.Linear(in_features=1280, out_features=1280, bias=False, device=target.device, dtype=target.dtype),
-                fl.Lambda(func=self.pool),
-            )
-            super().__init__(
-                target.ensure_find(CLIPTokenizer),
-                fl.SetContext(context=POOLING, key="end_of_text_index", callback=self.set_end_of_text_index),
-                target[1:-2],  # ids -> penultimate hidden states
-                fl.Parallel(fl.Identity(), head),
-            )
+            if projection is None:
+                projection = fl.Linear(in_features=1280, out_features=1280, bias=False, device=target.device, dtype=target.dtype)
+            body, top = target[1:-_TAIL], target[-_TAIL:]
+            probe = fl.SetContext(context=_POOLING, key=_POSITIONS, callback=self.set_end_of_text_index)
+            pooled = fl.Chain(top, projection, fl.Lambda(func=self.pool))
+            super().__init__(target.ensure_find(CLIPTokenizer), probe, body, fl.Parallel(fl.Identity(), pooled))
 
     def init_context(self) -> Contexts:
-        return {POOLING: {"end_of_text_index": []}}
+        return {_POOLING: {_POSITIONS: []}}
 
     def __call__(self, text: str | list[str]) -> tuple[Tensor, Tensor]:
         return super().__call__(text)
@@ -56,16 +56,13 @@ class TextEncoderWithPooling(fl.Chain, Adapter[CLIPTextEncoderG]):
         return self.ensure_find(CLIPTokenizer)
 
     def set_end_of_text_index(self, end_of_text_index: list[int], tokens: Tensor) -> None:
-        """Position of the first end-of-text token of every prompt (the bigG tokenizer pads with 0, so it is unique)."""
-        marks = tokens == self.tokenizer.end_of_text_token_id
-        for row in marks:
-            (position,) = row.nonzero(as_tuple=True)
-            end_of_text_index.append(cast(int, position.item()))
+        end_of_text_index.extend(first_end_of_text(tokens, self.tokenizer.end_of_text_token_id))
 
     def pool(self, x: Tensor) -> Tensor:
-        positions = self.use_context(context_name=POOLING).get("end_of_text_index", [])
+        positions = self.use_context(context_name=_POOLING).get(_POSITIONS, [])
         assert len(positions) == x.shape[0], "End of text index not found."
-        return torch.cat([x[i : i + 1, at, :] for i, at in enumerate(positions)], dim=0)
+        rows = torch.arange(x.shape[0], device=x.device)
+        return x[rows, torch.tensor(positions, device=x.device)]
 
 
 class DoubleTextEncoder(fl.Chain):
@@ -77,10 +74,14 @@ class DoubleTextEncoder(fl.Chain):
         device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        text_encoder_l = text_encoder_l or CLIPTextEncoderL(device=device, dtype=dtype)
-        text_encoder_g = text_encoder_g or CLIPTextEncoderG(device=device, dtype=dtype)
-        super().__init__(fl.Parallel(text_encoder_l[:-2], text_encoder_g), fl.Lambda(self.concatenate_embeddings))
-        TextEncoderWithPooling(target=text_encoder_g, projection=projection).inject(self.layer("Parallel", fl.Parallel))
+        small = text_encoder_l or CLIPTextEncoderL(device=device, dtype=dtype)
+        big = text_encoder_g or CLIPTextEncoderG(device=device, dtype=dtype)
+        super().__init__(fl.Parallel(small[:-_TAIL], big), fl.Lambda(self.concatenate_embeddings))
+        self._wrap_big_tower(self, big, projection)
+
+    @staticmethod
+    def _wrap_big_tower(owner: "DoubleTextEncoder", tower: CLIPTextEncoderG, projection: fl.Linear | None) -> None:
+        TextEncoderWithPooling(target=tower, projection=projection).inject(owner.layer("Parallel", fl.Parallel))
 
     def __call__(self, text: str | list[str]) -> tuple[Tensor, Tensor]:
         return super().__call__(text)
@@ -90,12 +91,14 @@ class DoubleTextEncoder(fl.Chain):
         return torch.cat((text_embedding_l, text_embedding_g), dim=-1), pooled_text_embedding
 
     def structural_copy(self: "DoubleTextEncoder") -> "DoubleTextEncoder":
-        """The pooling adapter refuses to be copied while injected: it is taken out, the plain tree copied, put back, and
-        a new adapter (sharing the projection) is built around the copy's bigG tower."""
+        """An injected adapter cannot be copied: the pooling adapter is taken out, the plain tree copied, the adapter put
+        back, and a new one - sharing the projection - built around the copy's bigG tower."""
         pooling = self.ensure_find(TextEncoderWithPooling)
+        shared_projection = pooling.layer(("Parallel", "Chain", "Linear"), fl.Linear)
         pooling.eject()
-        twin = super().structural_copy()
-        pooling.inject()
-        projection = pooling.layer(("Parallel", "Chain", "Linear"), fl.Linear)
-        TextEncoderWithPooling(target=twin.ensure_find(CLIPTextEncoderG), projection=projection).inject(twin.layer("Parallel", fl.Parallel))
+        try:
+            twin = super().structural_copy()
+        finally:
+            pooling.inject()
+        self._wrap_big_tower(twin, twin.ensure_find(CLIPTextEncoderG), shared_projection)
         return twin

@@ -40,43 +40,51 @@ from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.unet impor
 T = TypeVar("T", bound="SD1UNet | SDXLUNet")
 
 
+def reference_of(batch_size: int, device: torch.device | None = None) -> Tensor:
+    """Index of the image every image of a guidance batch borrows its style from: the first of its own half.
+    (half, half) images -> [0] * half + [half] * half."""
+    half = batch_size // 2
+    return torch.arange(batch_size, device=device).div(half, rounding_mode="floor") * half
+
+
+def token_statistics(x: Tensor) -> tuple[Tensor, Tensor]:
+    """Per (image, channel) mean and unbiased deviation over the tokens of [B, S, C], both [B, 1, C]."""
+    return x.mean(dim=-2, keepdim=True), x.std(dim=-2, keepdim=True)
+
+
 class ExtractReferenceFeatures(fl.Module):
-    """[2b, S, C] -> [2b, S, C]: image 0 of each guidance half, repeated over its half."""
+    """[2b, S, C] -> [2b, S, C]: every image replaced by the reference image of its half."""
 
     def forward(self, features: Tensor) -> Tensor:
-        half = features.shape[0] // 2
-        first, second = features.chunk(2, dim=0)
-        return torch.stack((first[0], second[0])).repeat_interleave(half, dim=0)
+        return features.index_select(0, reference_of(features.shape[0], features.device))
 
 
 class AdaIN(fl.Module):
-    """(targets, reference) -> (targets moved to the reference's per-channel token statistics, reference)."""
+    """(targets, reference) -> (targets standardised over their tokens, then given the reference's deviation and mean; reference)."""
 
     def __init__(self, epsilon: float = 1e-8) -> None:
         super().__init__()
         self.epsilon = epsilon
 
     def forward(self, targets: Tensor, reference: Tensor) -> tuple[Tensor, Tensor]:
-        def stats(x: Tensor) -> tuple[Tensor, Tensor]:
-            return torch.mean(x, dim=-2, keepdim=True), torch.std(x, dim=-2, keepdim=True)
-
-        centre, spread = stats(targets)
-        ref_centre, ref_spread = stats(reference)
-        return (targets - centre) / (spread + self.epsilon) * ref_spread + ref_centre, reference
+        mean, deviation = token_statistics(targets)
+        reference_mean, reference_deviation = token_statistics(reference)
+        standardised = (targets - mean) / (deviation + self.epsilon)
+        return standardised * reference_deviation + reference_mean, reference
 
 
 class ScaleReferenceFeatures(fl.Module):
-    """Multiply by ``scale`` every image but the first of each guidance half."""
+    """Multiply by ``scale`` every image that is not its own reference (the first of each half keeps factor 1)."""
 
     def __init__(self, scale: float = 1.0) -> None:
         super().__init__()
         self.scale = scale
 
     def forward(self, features: Tensor) -> Tensor:
-        half = features.shape[0] // 2
-        scaled = features.clone()
-        scaled.reshape(2, half, *features.shape[1:])[:, 1:] *= self.scale
-        return scaled
+        batch = features.shape[0]
+        own = reference_of(batch, features.device) == torch.arange(batch, device=features.device)
+        keep = own.reshape(batch, *([1] * (features.ndim - 1)))
+        return torch.where(keep, features, features * self.scale)
 
 
 class StyleAligned(fl.Chain):

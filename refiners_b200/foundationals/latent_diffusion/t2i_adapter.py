@@ -90,16 +90,24 @@ class StatefulResidualBlocks(fl.Chain):
         features.append(x)
 
 
-def _stem(in_channels: int, downscale_factor: int, width: int, where: dict[str, Any]) -> tuple[fl.Module, fl.Module]:
-    """Space-to-depth by ``downscale_factor`` and a 3x3 conv onto the first stage's width."""
-    return (
-        fl.PixelUnshuffle(downscale_factor=downscale_factor),
-        fl.Conv2d(in_channels=in_channels * downscale_factor**2, out_channels=width, kernel_size=3, padding=1, **where),
-    )
+def _encoder_layers(
+    in_channels: int, channels: tuple[int, int, int, int], num_residual_blocks: int, downscale_factor: int,
+    halving: tuple[bool, bool, bool, bool], where: dict[str, Any],
+) -> list[fl.Module]:
+    """Space-to-depth by ``downscale_factor``, a 3x3 stem onto the first width, four recorded stages (stage ``n`` halves the
+    resolution first if ``halving[n]``, and widens from the previous stage's width), and the read-out of what was recorded."""
+    unshuffle = fl.PixelUnshuffle(downscale_factor=downscale_factor)
+    stem = fl.Conv2d(in_channels=in_channels * downscale_factor**2, out_channels=channels[0], kernel_size=3, padding=1, **where)
+    incoming = (channels[0], *channels[:-1])
+    stages = [
+        StatefulResidualBlocks(narrow, wide, num_residual_blocks, downsample=halve, **where)
+        for narrow, wide, halve in zip(incoming, channels, halving)
+    ]
+    return [unshuffle, stem, *stages, fl.UseContext(context=CONTEXT, key="features")]
 
 
 class ConditionEncoder(fl.Chain):
-    """SD 1.5 layout: image / 8, then four stages, each after the first halving the resolution; returns the four stage outputs."""
+    """SD 1.5 layout: image / 8, then every stage after the first halves again (1/8, 1/16, 1/32, 1/64)."""
 
     def __init__(
         self, in_channels: int = 3, channels: tuple[int, int, int, int] = (320, 640, 1280, 1280), num_residual_blocks: int = 2,
@@ -107,16 +115,14 @@ class ConditionEncoder(fl.Chain):
     ) -> None:
         self.scale = scale
         where = {"device": device, "dtype": dtype}
-        stages = [StatefulResidualBlocks(channels[0], channels[0], num_residual_blocks, **where)]
-        stages += [StatefulResidualBlocks(narrow, wide, num_residual_blocks, downsample=True, **where) for narrow, wide in zip(channels, channels[1:])]
-        super().__init__(*_stem(in_channels, downscale_factor, channels[0], where), *stages, fl.UseContext(context=CONTEXT, key="features"))
+        super().__init__(*_encoder_layers(in_channels, channels, num_residual_blocks, downscale_factor, (False, True, True, True), where))
 
     def init_context(self) -> Contexts:
         return {CONTEXT: {"features": []}}
 
 
 class ConditionEncoderXL(ConditionEncoder, fl.Chain):
-    """SDXL layout: image / 16, four stages of which only the third halves the resolution (SDXL's UNet has three levels)."""
+    """SDXL layout: image / 16, and only the third stage halves (1/16, 1/16, 1/32, 1/32): SDXL's UNet has three levels."""
 
     def __init__(
         self, in_channels: int = 3, channels: tuple[int, int, int, int] = (320, 640, 1280, 1280), num_residual_blocks: int = 2,
@@ -124,12 +130,7 @@ class ConditionEncoderXL(ConditionEncoder, fl.Chain):
     ) -> None:
         self.scale = scale
         where = {"device": device, "dtype": dtype}
-        widths = (channels[0], *channels)
-        stages = [
-            StatefulResidualBlocks(narrow, wide, num_residual_blocks, downsample=(n == 2), **where)
-            for n, (narrow, wide) in enumerate(zip(widths, widths[1:]))
-        ]
-        fl.Chain.__init__(self, *_stem(in_channels, downscale_factor, channels[0], where), *stages, fl.UseContext(context=CONTEXT, key="features"))
+        fl.Chain.__init__(self, *_encoder_layers(in_channels, channels, num_residual_blocks, downscale_factor, (False, False, True, False), where))
 
 
 class T2IFeatures(fl.Residual):
@@ -153,23 +154,61 @@ class T2IFeatures(fl.Residual):
 
 
 class T2IAdapter(Generic[T], fl.Chain, Adapter[T]):
+    """Base of the per-family adapters.  A family states WHERE its four feature maps enter the UNet:
+
+      entry_blocks        indices into ``DownBlocks``: a `T2IFeatures` goes in front of that block's skip-connection tap
+      into_middle_block   whether the last feature map is appended to ``MiddleBlock`` instead (SDXL: three encoder levels)
+
+    and everything else - placing / removing the `T2IFeatures`, the scale, the condition context - is shared here."""
+
+    entry_blocks: tuple[int, ...] = ()
+    into_middle_block: bool = False
+
     _condition_encoder: list[ConditionEncoder]  # list-wrapped: the encoder is not a sub-module of the adapted UNet
     _features: list[T2IFeatures] = []
 
-    def __init__(self, target: T, name: str, condition_encoder: ConditionEncoder, weights: dict[str, Tensor] | None = None) -> None:
+    def __init__(
+        self, target: T, name: str, condition_encoder: ConditionEncoder, weights: dict[str, Tensor] | None = None, scale: float | None = None,
+    ) -> None:
         self.name = name
+        if scale is not None or not self._features:
+            count = len(self.entry_blocks) + int(self.into_middle_block)
+            self._features = [T2IFeatures(name=name, index=i, scale=1.0 if scale is None else scale) for i in range(count)]
+        self.residual_indices = self.entry_blocks
         if weights is not None:
             condition_encoder.load_state_dict(weights)
         self._condition_encoder = [condition_encoder]
         with self.setup_adapter(target):
             super().__init__(target)
 
+    # -- placement ---------------------------------------------------------------------------------------
+    def _entry_points(self) -> list[tuple[fl.Chain, T2IFeatures, bool]]:
+        """(block, feature layer, goes in front of the block's ResidualAccumulator?) for every feature map."""
+        from refiners_b200.foundationals.latent_diffusion.unet_blocks import ResidualAccumulator  # noqa: F401
+
+        points = [(self.target.layer(("DownBlocks", n), fl.Chain), layer, True) for n, layer in zip(self.entry_blocks, self._features)]
+        if self.into_middle_block:
+            points.append((self.target.layer("MiddleBlock", fl.Chain), self._features[-1], False))
+        return points
+
     def inject(self: TT2IAdapter, parent: fl.Chain | None = None) -> TT2IAdapter:
+        from refiners_b200.foundationals.latent_diffusion.unet_blocks import ResidualAccumulator
+
+        for block, layer, before_tap in self._entry_points():
+            for present in block.layers(layer_type=T2IFeatures):
+                assert present.name != self.name, f"T2I-Adapter named {self.name} is already injected"
+            if before_tap:
+                block.insert_before_type(ResidualAccumulator, layer)
+            else:
+                block.append(layer)
         return super().inject(parent)
 
     def eject(self) -> None:
+        for block, layer, _ in self._entry_points():
+            block.remove(layer)
         super().eject()
 
+    # -- condition ---------------------------------------------------------------------------------------
     @property
     def condition_encoder(self) -> ConditionEncoder:
         return self._condition_encoder[0]
@@ -180,6 +219,9 @@ class T2IAdapter(Generic[T], fl.Chain, Adapter[T]):
     def set_condition_features(self, features: tuple[Tensor, ...]) -> None:
         self.set_context(CONTEXT, {f"condition_features_{self.name}": features})
 
+    def init_context(self) -> Contexts:
+        return {CONTEXT: {f"condition_features_{self.name}": None}}
+
     @property
     def scale(self) -> float:
         return self._features[0].scale
@@ -189,13 +231,5 @@ class T2IAdapter(Generic[T], fl.Chain, Adapter[T]):
         for feature in self._features:
             feature.scale = value
 
-    def init_context(self) -> Contexts:
-        return {CONTEXT: {f"condition_features_{self.name}": None}}
-
     def structural_copy(self: TT2IAdapter) -> TT2IAdapter:
         raise RuntimeError("T2I-Adapter cannot be copied, eject it first.")
-
-    # -- where the features enter (shared by the per-family adapters) ----------------------------------------------
-    def _claim(self, block: fl.Chain) -> None:
-        for present in block.layers(layer_type=T2IFeatures):
-            assert present.name != self.name, f"T2I-Adapter named {self.name} is already injected"

@@ -72,3 +72,16 @@ def test_style_aligned_kernel(cuda_device, variant, dtype):
     eps = {torch.float32: 2e-6, torch.bfloat16: 2**-8, torch.float16: 2**-11}[dtype]
     assert (got.float().cpu() - want).abs().max().item() <= eps * want.abs().max().item()
     assert (generic.float() - got.float()).abs().max().item() <= 8 * eps * want.abs().max().item()
+
+
+@pytest.mark.skipif(not Path("/root/reference/src/refiners").exists(), reason="/root/reference is not mounted here")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=str)
+def test_style_aligned_chain_is_bit_identical_to_the_reference_on_the_host(dtype):
+    from oracle.pin_against_reference import _import_reference
+
+    _import_reference()
+    from refiners.foundationals.latent_diffusion.style_aligned import StyleAligned as Theirs
+
+    x = (torch.randn(6, 10, 16, generator=torch.Generator().manual_seed(0)) * 2 + 0.3).to(dtype)
+    for adain, concatenate in ((True, False), (True, True), (False, True), (False, False)):
+        assert torch.equal(StyleAligned(adain, concatenate, 0.7)(x), Theirs(adain, concatenate, 0.7)(x))
