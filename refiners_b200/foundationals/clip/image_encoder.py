@@ -10,8 +10,9 @@ for (head dim 80 for the H tower: the zero-padded tcgen05 attention path).
 
 from __future__ import annotations
 
+from typing import Any
+
 import torch
-from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
 from refiners_b200.foundationals.clip.common import FeedForward, PositionalEncoder
@@ -20,9 +21,22 @@ Device = torch.device
 DType = torch.dtype
 
 
+# published vision towers: (width, layers, heads, feed-forward width, output width); all see 224 x 224 images in 14 x 14 patches
+_TOWERS: dict[str, tuple[int, int, int, int, int]] = {
+    "H": (1280, 32, 16, 5120, 1024),  # OpenCLIP ViT-H/14  (head dim 80): IP-Adapter for SD 1.5 and the SDXL "vit-h" variants
+    "G": (1664, 48, 16, 8192, 1280),  # OpenCLIP ViT-bigG/14 (head dim 104): the first SDXL IP-Adapter
+}
+
+
+def _note(module: fl.Module, **hyper: Any) -> None:
+    """Constructor arguments kept on the module: ``repr`` echoes them, adapters read them."""
+    for name, value in hyper.items():
+        setattr(module, name, value)
+
+
 class ClassToken(fl.Chain):
     def __init__(self, embedding_dim: int, device: Device | str | None = None, dtype: DType | None = None) -> None:
-        self.embedding_dim = embedding_dim
+        _note(self, embedding_dim=embedding_dim)
         super().__init__(fl.Parameter(1, embedding_dim, device=device, dtype=dtype))
 
 
@@ -33,12 +47,10 @@ class PatchEncoder(fl.Chain):
         self, in_channels: int, out_channels: int, patch_size: int = 16, use_bias: bool = True,
         device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.in_channels, self.out_channels, self.patch_size, self.use_bias = in_channels, out_channels, patch_size, use_bias
-        super().__init__(
-            fl.Conv2d(in_channels, out_channels, kernel_size=(patch_size, patch_size), stride=(patch_size, patch_size),
-                      use_bias=use_bias, device=device, dtype=dtype),
-            fl.Permute(0, 2, 3, 1),
-        )
+        _note(self, in_channels=in_channels, out_channels=out_channels, patch_size=patch_size, use_bias=use_bias)
+        square = (patch_size, patch_size)
+        cut = fl.Conv2d(in_channels, out_channels, kernel_size=square, stride=square, use_bias=use_bias, device=device, dtype=dtype)
+        super().__init__(cut, fl.Permute(0, 2, 3, 1))
 
 
 class TransformerLayer(fl.Chain):
@@ -48,17 +60,14 @@ class TransformerLayer(fl.Chain):
         self, embedding_dim: int = 768, feedforward_dim: int = 3072, num_attention_heads: int = 12, layer_norm_eps: float = 1e-5,
         device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim, self.feedforward_dim = embedding_dim, feedforward_dim
-        self.num_attention_heads, self.layer_norm_eps = num_attention_heads, layer_norm_eps
-        kw = dict(device=device, dtype=dtype)
-
-        def norm() -> fl.LayerNorm:
-            return fl.LayerNorm(embedding_dim, eps=layer_norm_eps, **kw)
-
-        super().__init__(
-            fl.Residual(norm(), fl.SelfAttention(embedding_dim=embedding_dim, num_heads=num_attention_heads, **kw)),
-            fl.Residual(norm(), FeedForward(embedding_dim, feedforward_dim, **kw)),
+        _note(self, embedding_dim=embedding_dim, feedforward_dim=feedforward_dim, num_attention_heads=num_attention_heads,
+              layer_norm_eps=layer_norm_eps)
+        on: dict[str, Any] = {"device": device, "dtype": dtype}
+        mixers = (
+            fl.SelfAttention(embedding_dim=embedding_dim, num_heads=num_attention_heads, **on),
+            FeedForward(embedding_dim, feedforward_dim, **on),
         )
+        super().__init__(fl.Residual(fl.LayerNorm(embedding_dim, eps=layer_norm_eps, **on), mixer) for mixer in mixers)
 
 
 class ViTEmbeddings(fl.Chain):
@@ -68,13 +77,16 @@ class ViTEmbeddings(fl.Chain):
         self, image_size: int = 224, embedding_dim: int = 768, patch_size: int = 32, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.image_size, self.embedding_dim, self.patch_size = image_size, embedding_dim, patch_size
-        kw = dict(device=device, dtype=dtype)
-        grid = (image_size // patch_size) ** 2
-        patches = fl.Chain(PatchEncoder(3, embedding_dim, patch_size=patch_size, use_bias=False, **kw), fl.Reshape(grid, embedding_dim))
+        _note(self, image_size=image_size, embedding_dim=embedding_dim, patch_size=patch_size)
+        on: dict[str, Any] = {"device": device, "dtype": dtype}
+        patches_per_side = image_size // patch_size
+        count = patches_per_side * patches_per_side
+        patch_tokens = fl.Chain(
+            PatchEncoder(3, embedding_dim, patch_size=patch_size, use_bias=False, **on), fl.Reshape(count, embedding_dim),
+        )
         super().__init__(
-            fl.Concatenate(ClassToken(embedding_dim, **kw), patches, dim=1),
-            fl.Residual(PositionalEncoder(max_sequence_length=grid + 1, embedding_dim=embedding_dim, **kw)),
+            fl.Concatenate(ClassToken(embedding_dim, **on), patch_tokens, dim=1),
+            fl.Residual(PositionalEncoder(max_sequence_length=1 + count, embedding_dim=embedding_dim, **on)),
         )
 
 
@@ -95,35 +107,41 @@ class CLIPImageEncoder(fl.Chain):
         device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.image_size, self.embedding_dim, self.output_dim, self.patch_size = image_size, embedding_dim, output_dim, patch_size
-        self.num_layers, self.num_attention_heads, self.feedforward_dim = num_layers, num_attention_heads, feedforward_dim
-        kw = dict(device=device, dtype=dtype)
-        cls_token_pooling = lambda x: x[:, 0, :]  # noqa: E731  (the name shows in repr())
-        super().__init__(
-            ViTEmbeddings(image_size=image_size, embedding_dim=embedding_dim, patch_size=patch_size, **kw),
-            fl.LayerNorm(embedding_dim, eps=layer_norm_eps, **kw),
-            fl.Chain(
-                TransformerLayer(embedding_dim=embedding_dim, feedforward_dim=feedforward_dim,
-                                 num_attention_heads=num_attention_heads, layer_norm_eps=layer_norm_eps, **kw)
-                for _ in range(num_layers)
-            ),
-            fl.Lambda(func=cls_token_pooling),
-            fl.LayerNorm(embedding_dim, eps=layer_norm_eps, **kw),
-            fl.Linear(embedding_dim, output_dim, bias=False, **kw),
+        _note(self, image_size=image_size, embedding_dim=embedding_dim, output_dim=output_dim, patch_size=patch_size,
+              num_layers=num_layers, num_attention_heads=num_attention_heads, feedforward_dim=feedforward_dim)
+        on: dict[str, Any] = {"device": device, "dtype": dtype}
+
+        def norm() -> fl.LayerNorm:
+            return fl.LayerNorm(embedding_dim, eps=layer_norm_eps, **on)
+
+        trunk = fl.Chain(
+            TransformerLayer(embedding_dim, feedforward_dim, num_attention_heads, layer_norm_eps, **on) for _ in range(num_layers)
         )
+        super().__init__(
+            ViTEmbeddings(image_size=image_size, embedding_dim=embedding_dim, patch_size=patch_size, **on),
+            norm(),
+            trunk,
+            fl.Lambda(func=lambda x: x.select(1, 0)),  # the [CLS] row of every image; repr() prints "<lambda>(x)"
+            norm(),
+            fl.Linear(embedding_dim, output_dim, bias=False, **on),
+        )
+
+
+def _published(tag: str, device: Device | str | None, dtype: DType | None) -> dict[str, Any]:
+    width, layers, heads, hidden, out = _TOWERS[tag]
+    return dict(embedding_dim=width, output_dim=out, patch_size=14, num_layers=layers, num_attention_heads=heads,
+                feedforward_dim=hidden, device=device, dtype=dtype)
 
 
 class CLIPImageEncoderH(CLIPImageEncoder):
     """ViT-H/14: 1280 wide, 32 layers, 16 heads (d = 80), 1024-d output."""
 
     def __init__(self, device: Device | str | None = None, dtype: DType | None = None) -> None:
-        super().__init__(embedding_dim=1280, output_dim=1024, patch_size=14, num_layers=32, num_attention_heads=16,
-                         feedforward_dim=5120, device=device, dtype=dtype)
+        super().__init__(**_published("H", device, dtype))
 
 
 class CLIPImageEncoderG(CLIPImageEncoder):
     """ViT-bigG/14: 1664 wide, 48 layers, 16 heads (d = 104), 1280-d output."""
 
     def __init__(self, device: Device | str | None = None, dtype: DType | None = None) -> None:
-        super().__init__(embedding_dim=1664, output_dim=1280, patch_size=14, num_layers=48, num_attention_heads=16,
-                         feedforward_dim=8192, device=device, dtype=dtype)
+        super().__init__(**_published("G", device, dtype))

@@ -24,11 +24,30 @@ DType = torch.dtype
 _CTX = "dinov2_vit"
 
 
+def _note(module: fl.Module, **hyper: object) -> dict[str, object]:
+    """Record constructor arguments on the module (they are what ``repr`` echoes and what adapters read)."""
+    for name, value in hyper.items():
+        setattr(module, name, value)
+    return hyper
+
+
+def resample_positions(positions: Tensor, grid_hw: tuple[int, int], mode: str, antialias: bool) -> Tensor:
+    """``[B, 1 + s*s, D]`` learned positions -> ``[B, 1 + h*w, D]``: the square grid of patch positions is resized as an
+    image (in fp32 whatever the model dtype: the reference's vit.py:86-91 does the same), [CLS] keeps its row."""
+    batch, rows, dim = positions.shape
+    side = isqrt(rows - 1)
+    assert side * side == rows - 1, "The sequence length must be a square number."
+    as_image = positions[:, 1:, :].unflatten(1, (side, side)).movedim(-1, 1)
+    resized = interpolate(x=as_image.to(dtype=torch.float32), mode=mode, antialias=antialias, size=torch.Size(grid_hw))
+    patches = resized.to(dtype=positions.dtype).movedim(1, -1).reshape(batch, -1, dim)
+    return torch.cat((positions[:, :1, :], patches), dim=1)
+
+
 class ClassToken(fl.Chain):
     """The learnable [CLS] embedding, broadcast over the batch."""
 
     def __init__(self, embedding_dim: int, device: Device | str | None = None, dtype: DType | None = None) -> None:
-        self.embedding_dim = embedding_dim
+        _note(self, embedding_dim=embedding_dim)
         super().__init__(fl.Parameter(1, embedding_dim, device=device, dtype=dtype))
 
 
@@ -39,28 +58,20 @@ class PositionalEmbedding(fl.Chain):
         self, sequence_length: int, embedding_dim: int, patch_size: int, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.sequence_length, self.embedding_dim, self.patch_size = sequence_length, embedding_dim, patch_size
+        _note(self, sequence_length=sequence_length, embedding_dim=embedding_dim, patch_size=patch_size)
         super().__init__(fl.Parameter(sequence_length, embedding_dim, device=device, dtype=dtype))
 
 
 class InterpolateEmbedding(fl.Module):
-    """Resample the patch-position grid to the grid of the actual input image; [CLS] keeps its embedding.
-    The resize runs in fp32 whatever the model dtype (vit.py:86-91 in the reference)."""
+    """Resample the positions to the patch grid of the actual input image (`resample_positions`)."""
 
     def __init__(self, mode: str, antialias: bool, patch_size: int) -> None:
         super().__init__()
-        self.mode, self.antialias, self.patch_size = mode, antialias, patch_size
+        _note(self, mode=mode, antialias=antialias, patch_size=patch_size)
 
     def forward(self, x: Tensor, input: Tensor) -> Tensor:
-        cls, grid = x[:, :1, :], x[:, 1:, :]
-        batch, count, dim = grid.shape
-        side = isqrt(count)
-        assert side * side == count, "The sequence length must be a square number."
-        target = torch.Size((input.shape[2] // self.patch_size, input.shape[3] // self.patch_size))
-        grid = grid.reshape(batch, side, side, dim).permute(0, 3, 1, 2)
-        grid = interpolate(x=grid.to(dtype=torch.float32), mode=self.mode, antialias=self.antialias, size=target)
-        grid = grid.to(dtype=cls.dtype).permute(0, 2, 3, 1).reshape(batch, -1, dim)
-        return torch.cat((cls, grid), dim=1)
+        height, width = input.shape[-2:]
+        return resample_positions(x, (height // self.patch_size, width // self.patch_size), self.mode, self.antialias)
 
 
 class LayerScale(fl.WeightedModule):
@@ -71,11 +82,10 @@ class LayerScale(fl.WeightedModule):
     ) -> None:
         super().__init__()
         self.embedding_dim = embedding_dim
-        gain = torch.full(size=(embedding_dim,), fill_value=init_value, dtype=dtype, device=device)
-        self.register_parameter(name="weight", param=torch.nn.Parameter(gain))
+        self.weight = torch.nn.Parameter(torch.full((embedding_dim,), init_value, dtype=dtype, device=device))
 
     def forward(self, x: Tensor) -> Tensor:
-        return x * self.weight
+        return self.weight * x
 
 
 class FeedForward(fl.Chain):
@@ -85,10 +95,13 @@ class FeedForward(fl.Chain):
         self, embedding_dim: int, feedforward_dim: int, activation: fl.Activation, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim, self.feedforward_dim = embedding_dim, feedforward_dim
-        kw = dict(device=device, dtype=dtype)
-        expanded = 2 * feedforward_dim if isinstance(activation, fl.GLU) else feedforward_dim
-        super().__init__(fl.Linear(embedding_dim, expanded, **kw), activation, fl.Linear(feedforward_dim, embedding_dim, **kw))
+        _note(self, embedding_dim=embedding_dim, feedforward_dim=feedforward_dim)
+        gated = isinstance(activation, fl.GLU)
+        super().__init__(
+            fl.Linear(embedding_dim, feedforward_dim * (2 if gated else 1), device=device, dtype=dtype),
+            activation,
+            fl.Linear(feedforward_dim, embedding_dim, device=device, dtype=dtype),
+        )
 
 
 class PatchEncoder(fl.Chain):
@@ -99,13 +112,9 @@ class PatchEncoder(fl.Chain):
         self, in_channels: int, out_channels: int, patch_size: int, device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.in_channels, self.out_channels, self.patch_size = in_channels, out_channels, patch_size
-        super().__init__(
-            fl.SetContext(context=_CTX, key="input"),
-            fl.Conv2d(in_channels, out_channels, kernel_size=patch_size, stride=patch_size, device=device, dtype=dtype),
-            fl.Reshape(out_channels, -1),
-            fl.Transpose(1, 2),
-        )
+        _note(self, in_channels=in_channels, out_channels=out_channels, patch_size=patch_size)
+        to_patches = fl.Conv2d(in_channels, out_channels, kernel_size=patch_size, stride=patch_size, device=device, dtype=dtype)
+        super().__init__(fl.SetContext(context=_CTX, key="input"), to_patches, fl.Reshape(out_channels, -1), fl.Transpose(1, 2))
 
 
 class TransformerLayer(fl.Chain):
@@ -115,16 +124,15 @@ class TransformerLayer(fl.Chain):
         self, embedding_dim: int, num_heads: int, norm_eps: float, mlp_ratio: int, activation: fl.Activation,
         feedforward_dim: int | None = None, device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim, self.num_heads, self.norm_eps, self.mlp_ratio = embedding_dim, num_heads, norm_eps, mlp_ratio
-        self.feedforward_dim = feedforward_dim if feedforward_dim is not None else embedding_dim * mlp_ratio
-        kw = dict(device=device, dtype=dtype)
-
-        def branch(body: fl.Module) -> fl.Residual:
-            return fl.Residual(fl.LayerNorm(embedding_dim, eps=norm_eps, **kw), body, LayerScale(embedding_dim, **kw))
-
+        hidden = embedding_dim * mlp_ratio if feedforward_dim is None else feedforward_dim
+        _note(self, embedding_dim=embedding_dim, num_heads=num_heads, norm_eps=norm_eps, mlp_ratio=mlp_ratio, feedforward_dim=hidden)
+        on = dict(device=device, dtype=dtype)
+        mixers = (
+            fl.SelfAttention(embedding_dim=embedding_dim, num_heads=num_heads, **on),
+            FeedForward(embedding_dim, hidden, activation, **on),
+        )
         super().__init__(
-            branch(fl.SelfAttention(embedding_dim=embedding_dim, num_heads=num_heads, **kw)),
-            branch(FeedForward(embedding_dim, self.feedforward_dim, activation, **kw)),
+            fl.Residual(fl.LayerNorm(embedding_dim, eps=norm_eps, **on), mixer, LayerScale(embedding_dim, **on)) for mixer in mixers
         )
 
 
@@ -142,13 +150,9 @@ class Registers(fl.Concatenate):
     def __init__(
         self, num_registers: int, embedding_dim: int, device: Device | str | None = None, dtype: DType | None = None,
     ) -> None:
-        self.num_registers, self.embedding_dim = num_registers, embedding_dim
-        super().__init__(
-            fl.Slicing(dim=1, end=1),
-            fl.Parameter(num_registers, embedding_dim, device=device, dtype=dtype),
-            fl.Slicing(dim=1, start=1),
-            dim=1,
-        )
+        _note(self, num_registers=num_registers, embedding_dim=embedding_dim)
+        learned = fl.Parameter(num_registers, embedding_dim, device=device, dtype=dtype)
+        super().__init__(fl.Slicing(dim=1, end=1), learned, fl.Slicing(dim=1, start=1), dim=1)
 
 
 class ViT(fl.Chain):
@@ -171,29 +175,32 @@ class ViT(fl.Chain):
         device: Device | str | None = None,
         dtype: DType | None = None,
     ) -> None:
-        self.embedding_dim, self.patch_size, self.image_size = embedding_dim, patch_size, image_size
-        self.num_layers, self.num_heads, self.norm_eps, self.mlp_ratio = num_layers, num_heads, norm_eps, mlp_ratio
-        self.num_registers, self.feedforward_dim = num_registers, feedforward_dim
-        kw = dict(device=device, dtype=dtype)
-        grid = image_size // patch_size
-        tokens = fl.Concatenate(ClassToken(embedding_dim, **kw), PatchEncoder(3, embedding_dim, patch_size, **kw), dim=1)
-        positions = PositionalEncoder(
-            PositionalEmbedding(grid * grid + 1, embedding_dim, patch_size, **kw),
-            fl.Chain(
-                fl.Parallel(fl.Identity(), fl.UseContext(context=_CTX, key="input")),
-                InterpolateEmbedding(mode=interpolate_mode, antialias=interpolate_antialias, patch_size=patch_size),
+        _note(
+            self, embedding_dim=embedding_dim, patch_size=patch_size, image_size=image_size, num_layers=num_layers, num_heads=num_heads,
+            norm_eps=norm_eps, mlp_ratio=mlp_ratio, num_registers=num_registers, feedforward_dim=feedforward_dim,
+        )
+        on = dict(device=device, dtype=dtype)
+        learned_positions = PositionalEmbedding((image_size // patch_size) ** 2 + 1, embedding_dim, patch_size, **on)
+        stages: list[fl.Module] = [
+            fl.Concatenate(ClassToken(embedding_dim, **on), PatchEncoder(3, embedding_dim, patch_size, **on), dim=1),
+            PositionalEncoder(
+                learned_positions,
+                fl.Chain(
+                    fl.Parallel(fl.Identity(), fl.UseContext(context=_CTX, key="input")),
+                    InterpolateEmbedding(mode=interpolate_mode, antialias=interpolate_antialias, patch_size=patch_size),
+                ),
             ),
-        )
-        layers = Transformer(
-            TransformerLayer(
-                embedding_dim=embedding_dim, feedforward_dim=feedforward_dim, activation=activation, num_heads=num_heads,
-                mlp_ratio=mlp_ratio, norm_eps=norm_eps, **kw,
-            )
-            for _ in range(num_layers)
-        )
-        super().__init__(tokens, positions, layers, fl.LayerNorm(embedding_dim, eps=norm_eps, **kw))
+        ]
         if num_registers > 0:
-            self.insert_before_type(Transformer, Registers(num_registers, embedding_dim, **kw))
+            stages.append(Registers(num_registers, embedding_dim, **on))
+        stages.append(
+            Transformer(
+                TransformerLayer(embedding_dim, num_heads, norm_eps, mlp_ratio, activation, feedforward_dim=feedforward_dim, **on)
+                for _ in range(num_layers)
+            )
+        )
+        stages.append(fl.LayerNorm(embedding_dim, eps=norm_eps, **on))
+        super().__init__(*stages)
 
     def init_context(self) -> Contexts:
         return {_CTX: {"input": None}}
