@@ -16,7 +16,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-SOURCES = ["api.cu", "simt_gemm.cu", "simt_attention.cu", "norm_kernels.cu", "tc_gemm.cu", "tc_attention.cu", "tc_attention2.cu", "tc_attention_short.cu", "attn_probs.cu", "sam_attention.cu"]
+SOURCES = ["api.cu", "simt_gemm.cu", "simt_attention.cu", "norm_kernels.cu", "tc_gemm.cu", "tc_attention.cu", "tc_attention2.cu", "tc_attention_short.cu", "tc_attention_win.cu", "attn_probs.cu", "sam_attention.cu"]
 HEADERS = [HERE / "common.cuh", HERE / "tc_ptx.cuh", ROOT / "include" / "refiners_b200.h"]
 LIB = HERE / "librefiners_b200.so"
 NVCC_FLAGS = [

@@ -166,5 +166,8 @@ int tc_sdpa2(cudaStream_t st, const SdpaProblem& p);
 // single-pass kernel for short key sequences (tc_attention_short.cu): Sk <= 128, head dim <= 64, one K/V set, no bias
 bool tc_sdpa_short_supported(const SdpaProblem& p);
 int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p);
+// SAM's 14 x 14 windows (tc_attention_win.cu): head dim 65..80, decomposed relative-position bias, 196 queries = keys
+bool tc_sdpa_win_supported(const SdpaProblem& p);
+int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p);
 
 }  // namespace rb200

@@ -229,6 +229,7 @@ int sam_attention_impl(cudaStream_t st, int dtype, const void* qkv, const void* 
   p.scale = 1.0f / sqrtf(float(d));
   p.bias_h = bias; p.bias_w = nullptr; p.bias_H = Hh; p.bias_W = Ww;  // combined table, see rel_bias_kernel
   // tcgen05 path: head dim 80 runs as two 64-column slabs (TMA zero-fills columns 80..127)
+  if (kernel_mode() != 1 && tc_sdpa_win_supported(p)) return tc_sdpa_win(st, p);   // the 14 x 14 windows
   if (kernel_mode() != 1 && tc_sdpa_supported(p)) return tc_sdpa(st, p);
   return simt_sdpa(st, p);
 }

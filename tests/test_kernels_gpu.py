@@ -349,7 +349,13 @@ def test_sdpa(cuda_device, kernel_mode, dtype, case):
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=str)
-@pytest.mark.parametrize("geom", [(2, 14, 14, 4, 80), (1, 9, 5, 2, 80), (1, 16, 16, 3, 64), (1, 20, 20, 2, 32)], ids=str)
+@pytest.mark.parametrize(
+    "geom",
+    [(2, 14, 14, 4, 80), (1, 9, 5, 2, 80), (1, 16, 16, 3, 64), (1, 20, 20, 2, 32),
+     # SAM's 14 x 14 windows on tc_attention_win.cu: more (window, head) items than SMs, head dim 72, one single item
+     (50, 14, 14, 16, 80), (3, 14, 14, 2, 72), (1, 14, 14, 1, 80)],
+    ids=str,
+)
 def test_sam_attention(cuda_device, kernel_mode, dtype, geom):
     """Decomposed relative-position attention (segment_anything/image_encoder.py:87-143 in the
     reference): logits = q k^T d^-1/2 + rel_h[q, kh] + rel_w[q, kw]."""

@@ -71,10 +71,11 @@ elif which == "attn77_dual":  # IP-Adapter: text cross-attention + 4 image token
     k, v = torch.randn(Bn, 77, H * 64, device=dev, dtype=bf), torch.randn(Bn, 77, H * 64, device=dev, dtype=bf)
     k2, v2 = torch.randn(Bn, 4, H * 64, device=dev, dtype=bf), torch.randn(Bn, 4, H * 64, device=dev, dtype=bf)
     fn, flops = (lambda: B.sdpa(q, k, v, H, k2=k2, v2=v2, scale2=0.6)), 4.0 * Bn * H * S * 81 * 64
-elif which == "attn_sam_win":
-    qkv = torch.randn(25, 14, 14, 3 * 1280, device=dev, dtype=bf)
+elif which in ("attn_sam_win", "attn_sam_win4"):  # the windowed blocks of SAM ViT-H at batch 1 / batch 4 (rel-pos tables + attention)
+    nwin = 25 if which == "attn_sam_win" else 100
+    qkv = torch.randn(nwin, 14, 14, 3 * 1280, device=dev, dtype=bf)
     rh, rw = torch.randn(27, 80, device=dev, dtype=bf), torch.randn(27, 80, device=dev, dtype=bf)
-    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * 25 * 16 * 196 * 196 * 80
+    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * nwin * 16 * 196 * 196 * 80
 elif which == "attn_sam_global":
     qkv = torch.randn(1, 64, 64, 3 * 1280, device=dev, dtype=bf)
     rh, rw = torch.randn(127, 80, device=dev, dtype=bf), torch.randn(127, 80, device=dev, dtype=bf)
