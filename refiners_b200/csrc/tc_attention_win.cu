@@ -21,9 +21,16 @@
 //     [row][30-float] table (LDS.64 pairs feed the packed FFMA2 directly; 30-word pitch: conflict free per half warp);
 //     the global loads for the NEXT window are issued before the current one is written out.
 //
+// GEOM 1 is the same kernel for SAM's four GLOBAL-attention blocks (64 x 64 tokens, any map whose rows are 64 wide):
+// a 128-key tile is two full rows of the map, so a thread's 64 columns are kw = 0..63 of ONE kh.  rel_w[q, 0..63]
+// (times log2 e) sits in the table as fp16 (136-byte rows; fp32 would need 64 KB for the two query tiles, fp16 keeps
+// 11 bits of a value that is added to logits rounded to bf16 anyway), rel_h[q, kh] is one fp32 scalar per key tile,
+// read from global one tile ahead and folded into the maximum / the exponent offset instead of into every logit.
+//
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
-// smem: Q 2 x 20 KB, K/V ring 2 x 40 KB, P 2 x 32 KB, bias 30 KB, 4 KB exchange.
+// smem: Q 2 x 20 KB, K/V ring 2 x 40 KB, P 2 x 32 KB, bias 30 KB (34 KB for GEOM 1), 4 KB exchange.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <type_traits>
@@ -40,7 +47,6 @@ constexpr int QT = 128;             // queries per tile (UMMA M)
 constexpr int KT = 128;             // keys per tile
 constexpr int WIN = 14;             // window side
 constexpr int SK = WIN * WIN;       // 196 keys = queries
-constexpr int NTILES = 2;           // key tiles per window
 constexpr int STAGES = 2;
 constexpr int NUM_THREADS = 640;
 constexpr int SLAB0 = QT * 128;     // 64 columns, 128-byte rows
@@ -51,11 +57,14 @@ constexpr int STAGE_BYTES = 2 * TILE_BYTES;        // K tile + V tile
 constexpr int P_SLAB = QT * 64 * 2;
 constexpr int P_BYTES = 2 * P_SLAB;
 constexpr int BIAS_PITCH = 30;                     // floats per query row: [0,14) rel_w, [14,28) rel_h, both times log2 e
-constexpr int BIAS_BYTES = 2 * QT * BIAS_PITCH * 4;
+constexpr int BIAS_PITCH_G = 136;                  // GEOM 1: bytes per query row, 64 fp16 rel_w entries (+ 8 B: conflict-free LDS.64)
+template <int GEOM> constexpr int bias_bytes() { return GEOM == 0 ? 2 * QT * BIAS_PITCH * 4 : 2 * QT * BIAS_PITCH_G; }
 constexpr int TMEM_COLS = 512;
 constexpr int XCHG_BYTES = 2 * 2 * 2 * QT * 4;
-constexpr size_t SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + 1024 + 256 + XCHG_BYTES + BIAS_BYTES;
-static_assert(SMEM_BYTES <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
+template <int GEOM> constexpr size_t smem_bytes() {
+  return Q_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + 1024 + 256 + XCHG_BYTES + bias_bytes<GEOM>();
+}
+static_assert(smem_bytes<0>() <= 227 * 1024 && smem_bytes<1>() <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr float L2E = 1.4426950408889634f;
 
@@ -63,11 +72,14 @@ struct WinParams {
   void* o;
   int64_t o_sb, o_ss;
   int H;
-  int64_t total_work;   // windows x heads
+  int64_t total_work;   // windows x heads (GEOM 1: images x heads x query-tile pairs)
+  int n_pairs;          // pairs of 128-query tiles per (image, head): 1 for a window
+  int ntiles;           // 128-key tiles: 2 for a window
+  int bias_H;           // rows of the map (GEOM 1)
   float scale_log2e;
   uint32_t idesc_qk, idesc_pv64, idesc_pv16;
   int d_out;
-  const float* bias;    // [window * H + head][2 query tiles][14 rel_h + 14 rel_w][128] (sam_attention.cu)
+  const float* bias;    // [window * H + head][query tile][bias_H rel_h + bias_W rel_w][128] (sam_attention.cu)
 };
 
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -108,7 +120,7 @@ __device__ __forceinline__ void st_shared_b64(uint32_t addr, float lo, float hi)
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(lo), "f"(hi) : "memory");
 }
 
-template <typename T>
+template <typename T, int GEOM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                    const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_k1,
@@ -130,7 +142,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   uint64_t* bar_ofree = q_full + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 12);
   float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
-  float* sBias = xchg + XCHG_BYTES / 4;         // [2 groups][128 rows][BIAS_PITCH]
+  float* sBias = xchg + XCHG_BYTES / 4;         // [2 groups][128 rows][BIAS_PITCH floats | BIAS_PITCH_G bytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = warp >> 2;
@@ -172,10 +184,11 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         uint32_t phase = 0;
         uint32_t n = 0;
         for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
-          const int h = int(w % p.H);
-          const int b = int(w / p.H);
+          const int pair = int(w % p.n_pairs);
+          const int h = int((w / p.n_pairs) % p.H);
+          const int b = int(w / (int64_t(p.n_pairs) * p.H));
 #pragma unroll 1
-          for (int j = 0; j < NTILES; ++j) {
+          for (int j = 0; j < p.ntiles; ++j) {
             mbar_wait(&kv_empty[stage], phase ^ 1, 2);
             mbar_arrive_expect_tx(&kv_full[stage], STAGE_BYTES);
             uint8_t* st = sKV + stage * STAGE_BYTES;
@@ -194,8 +207,8 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
               mbar_arrive_expect_tx(q_full, Q_BYTES);
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
-                tma_load_4d(sQ + g * TILE_BYTES, &map_q0, q_full, 0, h, g * QT, b);
-                tma_load_4d(sQ + g * TILE_BYTES + SLAB0, &map_q1, q_full, 64, h, g * QT, b);
+                tma_load_4d(sQ + g * TILE_BYTES, &map_q0, q_full, 0, h, (pair * 2 + g) * QT, b);
+                tma_load_4d(sQ + g * TILE_BYTES + SLAB0, &map_q1, q_full, 64, h, (pair * 2 + g) * QT, b);
               }
             }
           }
@@ -235,12 +248,12 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
           issue_s(st_k);
           next_k();
 #pragma unroll 1
-          for (int j = 0; j < NTILES; ++j) {
-            if (j + 1 < NTILES) {
+          for (int j = 0; j < p.ntiles; ++j) {
+            if (j + 1 < p.ntiles) {
               mbar_wait(&kv_full[st_k], ph_k, 6);
               issue_s(st_k);
               next_k();
-              if (j + 2 == NTILES) umma_commit(q_empty);   // the window's last S has been issued: Q frees when it retires (count 2)
+              if (j + 2 == p.ntiles) umma_commit(q_empty);   // the window's last S has been issued: Q frees when it retires (count 2)
             }
             mbar_wait(&bar_p[g], t & 1, 7);
             if (j == 0 && n > 0) mbar_wait(&bar_ofree[g], (n - 1) & 1, 8);
@@ -249,7 +262,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
             const uint64_t dv0 = desc_mnmajor(vb, SLAB0), dv1 = desc_sw32(vb + SLAB0);
 #pragma unroll
             for (int k = 0; k < KT / 16; ++k) {
-              if (j > 0 && k * 16 >= SK - KT) break;   // the second tile holds 68 keys: 5 k-steps
+              if (GEOM == 0 && j > 0 && k * 16 >= SK - KT) break;   // a window's second tile holds 68 keys: 5 k-steps
               const uint64_t dp = desc_kmajor(pbase + (k >> 2) * P_SLAB) + uint64_t((k & 3) * 2);
               const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
               umma_f16(tmem_o, dp, dv0 + uint64_t(k * 128), p.idesc_pv64, acc);        // 16 key rows x 128 B
@@ -282,33 +295,56 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
     const uint32_t a_o = smem_u32(&bar_o[g]), a_ofree = smem_u32(&bar_ofree[g]);
     const uint32_t swz = uint32_t(sw) << 4;
     const uint32_t xbar = 1 + g;
-    const uint32_t brow = smem_u32(sBias + (g * QT + row) * BIAS_PITCH);   // this query's bias rows
-    const bool live = g * QT + row < SK;                                    // the query exists
+    const uint32_t brow = smem_u32(sBias) + uint32_t(g * QT + row) * (GEOM == 0 ? BIAS_PITCH * 4 : BIAS_PITCH_G);   // this query's bias row
+    const bool live = GEOM == 1 || g * QT + row < SK;                       // the query exists
     T* obase = static_cast<T*>(p.o);
     uint32_t t = 0, n = 0;
+    const int nqt = 2 * p.n_pairs, bias_K = GEOM == 0 ? 2 * WIN : p.bias_H + 64;
 
-    // this thread's half of the NEXT window's bias rows (hf 0: the 14 rel_w entries, hf 1: the 14 rel_h entries)
-    float nb[WIN];
+    // GEOM 0: this thread's half of the NEXT window's bias rows (hf 0: the 14 rel_w entries, hf 1: the 14 rel_h entries)
+    float nb[GEOM == 0 ? WIN : 1];
     auto fetch_bias = [&](int64_t w) {
       const float* blk = p.bias + ((w * 2 + g) * (2 * WIN) + (hf == 0 ? WIN : 0)) * 128 + row;
 #pragma unroll
       for (int i = 0; i < WIN; ++i) nb[i] = live ? __ldg(blk + i * 128) : 0.f;
     };
-    if (int64_t(blockIdx.x) < p.total_work) fetch_bias(blockIdx.x);
+    if constexpr (GEOM == 0) fetch_bias(blockIdx.x);
 
     for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
-      const int h = int(w % p.H);
-      const int64_t b = w / p.H;
+      const int pair = int(w % p.n_pairs);
+      const int h = int((w / p.n_pairs) % p.H);
+      const int64_t b = w / (int64_t(p.n_pairs) * p.H);
+      // this query tile's block of the bias table: [bias_H rel_h rows | bias_W rel_w rows][128 queries]
+      const float* blk = p.bias + (((w / p.n_pairs) * nqt + pair * 2 + g) * bias_K) * 128 + row;
+      float bh_cur = 0.f;
       // publish the bias rows (the group's previous reads of the table ended before its last named barrier)
+      if constexpr (GEOM == 0) {
 #pragma unroll
-      for (int i = 0; i < WIN; i += 2) st_shared_b64(brow + uint32_t((hf == 0 ? 0 : WIN) + i) * 4, nb[i] * L2E, nb[i + 1] * L2E);
+        for (int i = 0; i < WIN; i += 2) st_shared_b64(brow + uint32_t((hf == 0 ? 0 : WIN) + i) * 4, nb[i] * L2E, nb[i + 1] * L2E);
+      } else {
+        // rel_w[q, hf * 32 .. + 32) as fp16; rel_h of the first key tile
+        const float* bw = blk + (p.bias_H + hf * 32) * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const __half2 lo = __floats2half2_rn(__ldg(bw + (c * 4) * 128) * L2E, __ldg(bw + (c * 4 + 1) * 128) * L2E);
+          const __half2 hi = __floats2half2_rn(__ldg(bw + (c * 4 + 2) * 128) * L2E, __ldg(bw + (c * 4 + 3) * 128) * L2E);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(brow + uint32_t(hf * 64 + c * 8)), "r"(*reinterpret_cast<const uint32_t*>(&lo)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&hi))
+                       : "memory");
+        }
+        bh_cur = __ldg(blk + hf * 128) * L2E;
+      }
       named_bar_sync(xbar, 256);
       float m_run = -INFINITY, l_run = 0.f;
 
-      auto tile = [&](auto jc, auto hc) {
+      // One key tile.  GEOM 0: J (key tile) and HF (column half) are compile-time, so every logit's (kh, kw) and whether its
+      // key exists are constants.  GEOM 1: J = HF = -1, `j` is the run-time tile index and all 64 columns are kw = 0..63 of
+      // the map row kh = 2 j + hf.
+      auto tile = [&](auto jc, auto hc, int j) {
         constexpr int J = decltype(jc)::value, HF = decltype(hc)::value;
-        constexpr int K0 = J * KT + HF * 64;                       // first key of this thread's 64 columns
-        constexpr int NV = SK - K0 >= 64 ? 64 : (SK - K0 > 0 ? SK - K0 : 0);   // keys that exist among them (even)
+        constexpr int K0 = J * KT + HF * 64;                       // GEOM 0: first key of this thread's 64 columns
+        constexpr int NV = GEOM == 1 ? 64 : (SK - K0 >= 64 ? 64 : (SK - K0 > 0 ? SK - K0 : 0));   // keys that exist among them (even)
+        const bool first = GEOM == 0 ? J == 0 : j == 0;
         mbar_wait_a(a_s, t & 1);
         tcgen05_fence_after();
         float s[64];
@@ -326,25 +362,41 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed_a(a_sfree);
-        // logits in the log2 domain: s * scale * log2 e + rel_w[kw] + rel_h[kh] (the table holds both times log2 e)
+        // logits in the log2 domain: s * scale * log2 e + rel_w[kw] (+ rel_h[kh]); the table holds the bias times log2 e
         const uint64_t sc2 = f32x2(p.scale_log2e, p.scale_log2e);
-        float tm0 = -INFINITY, tm1 = -INFINITY;
+        float tm0 = -INFINITY, tm1 = -INFINITY, bh = 0.f;
+        if constexpr (GEOM == 0) {
 #pragma unroll
-        for (int i = 0; i < NV; i += 2) {
-          const int k = K0 + i, kh = k / WIN, kw = k % WIN;         // constants after unrolling; kw is even
-          const float bh = ld_shared_f32_nv(brow + uint32_t(WIN + kh) * 4);
-          const uint64_t x = add_f32x2(fma_f32x2(f32x2(s[i], s[i + 1]), sc2, ld_shared_b64(brow + uint32_t(kw) * 4)), f32x2(bh, bh));
-          f32x2_split(x, s[i], s[i + 1]);
-          if ((i >> 1) & 1) tm1 = fmaxf(tm1, fmaxf(s[i], s[i + 1]));
-          else tm0 = fmaxf(tm0, fmaxf(s[i], s[i + 1]));
+          for (int i = 0; i < NV; i += 2) {
+            const int k = K0 + i, kh = k / WIN, kw = k % WIN;         // constants after unrolling; kw is even
+            const float bhv = ld_shared_f32_nv(brow + uint32_t(WIN + kh) * 4);
+            const uint64_t x = add_f32x2(fma_f32x2(f32x2(s[i], s[i + 1]), sc2, ld_shared_b64(brow + uint32_t(kw) * 4)), f32x2(bhv, bhv));
+            f32x2_split(x, s[i], s[i + 1]);
+            if ((i >> 1) & 1) tm1 = fmaxf(tm1, fmaxf(s[i], s[i + 1]));
+            else tm0 = fmaxf(tm0, fmaxf(s[i], s[i + 1]));
+          }
+        } else {
+          bh = bh_cur;   // rel_h[q, 2 j + hf]: the same for all 64 columns - it joins the maximum and the exponent offset
+          if (j + 1 < p.ntiles) bh_cur = __ldg(blk + (2 * (j + 1) + hf) * 128) * L2E;   // in flight during this tile
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const uint64_t h4 = ld_shared_b64(brow + uint32_t(i) * 2);
+            const uint32_t lo = uint32_t(h4), hi = uint32_t(h4 >> 32);
+            const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+            const float2 b23 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+            f32x2_split(fma_f32x2(f32x2(s[i], s[i + 1]), sc2, f32x2(b01.x, b01.y)), s[i], s[i + 1]);
+            f32x2_split(fma_f32x2(f32x2(s[i + 2], s[i + 3]), sc2, f32x2(b23.x, b23.y)), s[i + 2], s[i + 3]);
+            tm0 = fmaxf(tm0, fmaxf(s[i], s[i + 1]));
+            tm1 = fmaxf(tm1, fmaxf(s[i + 2], s[i + 3]));
+          }
         }
         const uint32_t slot = (t & 1) * (2 * QT * 4);
-        const float mine = fmaxf(tm0, tm1);
+        const float mine = fmaxf(tm0, tm1) + bh;
         st_shared_f32(x_mine + slot, mine);
         named_bar_sync(xbar, 256);
         const float tmax = fmaxf(mine, ld_shared_f32(x_other + slot));
         bool waited_o = false;
-        if constexpr (J == 0) {
+        if (first) {
           m_run = tmax;
         } else {
           const float m_new = fmaxf(m_run, tmax);
@@ -360,7 +412,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
             tmem_st_32x32(tmem_o, raw);
-            if constexpr (HF == 0) {
+            if (hf == 0) {
               uint32_t r2[16];
               tmem_ld_32x16(tmem_o1, r2);
               tmem_ld_wait();
@@ -373,10 +425,10 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
             m_run = m_new;
           }
         }
-        if ((J > 0 && !waited_o) || (J == 0 && t > 0)) mbar_wait_a(a_o, (t - 1) & 1);   // P buffer free
+        if ((!first && !waited_o) || (first && t > 0)) mbar_wait_a(a_o, (t - 1) & 1);   // P buffer free
         if (g == 1) named_bar_sync(3, 512);                                              // turnstile, see tc_attention2.cu
         else if (t > 0) named_bar_sync(4, 512);
-        const uint64_t nm2 = f32x2(-m_run, -m_run);
+        const uint64_t nm2 = f32x2(bh - m_run, bh - m_run);
         uint64_t sum_a = f32x2(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -415,16 +467,20 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         if (lane == 0) mbar_arrive_a(a_p);
         ++t;
       };
-      if (hf == 0) {
-        tile(std::integral_constant<int, 0>(), std::integral_constant<int, 0>());
-        tile(std::integral_constant<int, 1>(), std::integral_constant<int, 0>());
+      if constexpr (GEOM == 0) {
+        if (hf == 0) {
+          tile(std::integral_constant<int, 0>(), std::integral_constant<int, 0>(), 0);
+          tile(std::integral_constant<int, 1>(), std::integral_constant<int, 0>(), 1);
+        } else {
+          tile(std::integral_constant<int, 0>(), std::integral_constant<int, 1>(), 0);
+          tile(std::integral_constant<int, 1>(), std::integral_constant<int, 1>(), 1);
+        }
+        // next window's bias rows: in flight while this one is written out
+        if (w + gridDim.x < p.total_work) fetch_bias(w + gridDim.x);
       } else {
-        tile(std::integral_constant<int, 0>(), std::integral_constant<int, 1>());
-        tile(std::integral_constant<int, 1>(), std::integral_constant<int, 1>());
+#pragma unroll 1
+        for (int j = 0; j < p.ntiles; ++j) tile(std::integral_constant<int, -1>(), std::integral_constant<int, -1>(), j);
       }
-
-      // next window's bias rows: in flight while this one is written out
-      if (w + gridDim.x < p.total_work) fetch_bias(w + gridDim.x);
 
       const uint32_t slot = (t & 1) * (2 * QT * 4);
       st_shared_f32(x_mine + slot, l_run);
@@ -451,7 +507,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_a(a_ofree);
       if (live) {
-        const int64_t qi = int64_t(g) * QT + row;
+        const int64_t qi = (int64_t(pair) * 2 + g) * QT + row;
         T* dst = obase + b * p.o_sb + qi * p.o_ss + int64_t(h) * p.d_out;   // 16-byte aligned: checked on the host
         uint4* d0 = reinterpret_cast<uint4*>(dst + hf * 32);
 #pragma unroll
@@ -523,34 +579,45 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T>
+template <typename T, int GEOM>
 int launch(cudaStream_t st, const CUtensorMap (&m)[6], const WinParams& prm) {
   static PerDeviceOnce configured;
   if (configured.needed()) {
-    if (cudaFuncSetAttribute(tc_sdpa_win_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)) != cudaSuccess)
-      RB200_FAIL(-2, "tc_sdpa_win: cannot reserve %zu bytes of shared memory", SMEM_BYTES);
+    if (cudaFuncSetAttribute(tc_sdpa_win_kernel<T, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes<GEOM>())) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa_win: cannot reserve %zu bytes of shared memory", smem_bytes<GEOM>());
     configured.done();
   }
   const int64_t cap = sm_count();
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_win_kernel<T><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], prm);
+  tc_sdpa_win_kernel<T, GEOM><<<grid, NUM_THREADS, smem_bytes<GEOM>(), st>>>(m[0], m[1], m[2], m[3], m[4], m[5], prm);
   RB200_CHECK_LAUNCH("tc_sdpa_win");
   return 0;
 }
 
+// 0: a 14 x 14 window, 1: a map with 64-wide rows (an even number of them), -1: neither
+int geometry(const SdpaProblem& p) {
+  if (p.bias_H == WIN && p.bias_W == WIN && p.Sq == SK && p.Sk == SK) return 0;
+  if (p.bias_W == 64 && p.bias_H >= 4 && p.bias_H % 4 == 0 && p.Sk == int64_t(p.bias_H) * 64 && p.Sq == p.Sk) return 1;
+  return -1;
+}
+
 }  // namespace
 
-// RB200_ATTN_WIN: 0 = SAM's windows stay on the first-generation kernel, 1 (default) = this kernel.
+// RB200_ATTN_WIN: 0 = SAM's attention stays on the first-generation kernel, 1 = only the 14 x 14 windows run here,
+// 2 (default) = the windows and the global (64-wide map) blocks.
 bool tc_sdpa_win_supported(const SdpaProblem& p) {
   static const int enabled = [] {
     const char* e = getenv("RB200_ATTN_WIN");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 2;
   }();
   if (!enabled) return false;
   if (p.dtype != RB200_BF16 && p.dtype != RB200_FP16) return false;
   if (p.D <= 64 || p.D > 80 || (p.D & 7) != 0 || p.causal) return false;
-  if (p.bias_h == nullptr || p.bias_H != WIN || p.bias_W != WIN || p.Sq != SK || p.Sk != SK) return false;
-  if (p.k2 != nullptr || p.B < 1) return false;
+  if (p.bias_h == nullptr || p.k2 != nullptr || p.B < 1) return false;
+  const int geom = geometry(p);
+  if (geom < 0 || (geom == 1 && enabled < 2)) return false;
+  // the fp16 rel_w table of GEOM 1 carries 11 bits: below bf16's own rounding of the probabilities, not below fp16's
+  if (geom == 1 && p.dtype != RB200_BF16) return false;
   if ((reinterpret_cast<uintptr_t>(p.o) & 15) != 0 || p.o_ss % 8 != 0 || p.o_sb % 8 != 0) return false;
   return ok_operand(p.q, p.q_sb, p.q_ss) && ok_operand(p.k, p.k_sb, p.k_ss) && ok_operand(p.v, p.v_sb, p.v_ss);
 }
@@ -560,15 +627,19 @@ int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p) {
   const void* base[3] = {p.q, p.k, p.v};
   const int64_t sb[3] = {p.q_sb, p.k_sb, p.v_sb}, ss[3] = {p.q_ss, p.k_ss, p.v_ss};
   for (int i = 0; i < 3; ++i) {
-    if (int rc = make_map(&m[2 * i], p.dtype, base[i], p.B, SK, p.H, sb[i], ss[i], p.D, 64)) return rc;
-    if (int rc = make_map(&m[2 * i + 1], p.dtype, base[i], p.B, SK, p.H, sb[i], ss[i], p.D, 16)) return rc;
+    if (int rc = make_map(&m[2 * i], p.dtype, base[i], p.B, p.Sk, p.H, sb[i], ss[i], p.D, 64)) return rc;
+    if (int rc = make_map(&m[2 * i + 1], p.dtype, base[i], p.B, p.Sk, p.H, sb[i], ss[i], p.D, 16)) return rc;
   }
+  const int geom = geometry(p);
   WinParams prm{};
   prm.o = p.o;
   prm.o_sb = p.o_sb;
   prm.o_ss = p.o_ss;
   prm.H = p.H;
-  prm.total_work = int64_t(p.H) * p.B;
+  prm.n_pairs = int(ceil_div(p.Sq, 2 * QT));
+  prm.ntiles = int(ceil_div(p.Sk, KT));
+  prm.bias_H = p.bias_H;
+  prm.total_work = int64_t(p.H) * p.B * prm.n_pairs;
   prm.scale_log2e = p.scale * L2E;
   const uint32_t fmt = p.dtype == RB200_BF16 ? 1u : 0u;
   const uint32_t common = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(QT >> 4) << 24);
@@ -577,7 +648,9 @@ int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_pv16 = common | (uint32_t(16 >> 3) << 17) | (1u << 16);   // D = 128 x 16
   prm.d_out = p.D;
   prm.bias = p.bias_h;
-  return p.dtype == RB200_BF16 ? launch<__nv_bfloat16>(st, m, prm) : launch<__half>(st, m, prm);
+  const bool bf = p.dtype == RB200_BF16;
+  if (geom == 0) return bf ? launch<__nv_bfloat16, 0>(st, m, prm) : launch<__half, 0>(st, m, prm);
+  return bf ? launch<__nv_bfloat16, 1>(st, m, prm) : launch<__half, 1>(st, m, prm);
 }
 
 }  // namespace rb200

@@ -353,7 +353,9 @@ def test_sdpa(cuda_device, kernel_mode, dtype, case):
     "geom",
     [(2, 14, 14, 4, 80), (1, 9, 5, 2, 80), (1, 16, 16, 3, 64), (1, 20, 20, 2, 32),
      # SAM's 14 x 14 windows on tc_attention_win.cu: more (window, head) items than SMs, head dim 72, one single item
-     (50, 14, 14, 16, 80), (3, 14, 14, 2, 72), (1, 14, 14, 1, 80)],
+     (50, 14, 14, 16, 80), (3, 14, 14, 2, 72), (1, 14, 14, 1, 80),
+     # the global blocks (64-wide maps) on the same kernel: the full 64 x 64 map, a short one with two query-tile pairs
+     (1, 64, 64, 2, 80), (2, 8, 64, 3, 72)],
     ids=str,
 )
 def test_sam_attention(cuda_device, kernel_mode, dtype, geom):

@@ -76,10 +76,10 @@ elif which in ("attn_sam_win", "attn_sam_win4"):  # the windowed blocks of SAM V
     qkv = torch.randn(nwin, 14, 14, 3 * 1280, device=dev, dtype=bf)
     rh, rw = torch.randn(27, 80, device=dev, dtype=bf), torch.randn(27, 80, device=dev, dtype=bf)
     fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * nwin * 16 * 196 * 196 * 80
-elif which == "attn_sam_global":
-    qkv = torch.randn(1, 64, 64, 3 * 1280, device=dev, dtype=bf)
+elif which in ("attn_sam_global", "attn_sam_global4"):
+    qkv = torch.randn(1 if which == "attn_sam_global" else 4, 64, 64, 3 * 1280, device=dev, dtype=bf)
     rh, rw = torch.randn(127, 80, device=dev, dtype=bf), torch.randn(127, 80, device=dev, dtype=bf)
-    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * 16 * 4096 * 4096 * 80
+    fn, flops = (lambda: B.sam_attention(qkv, rh, rw, 16)), 4.0 * qkv.shape[0] * 16 * 4096 * 4096 * 80
 elif which in ("attn", "attn4096"):
     Bn, H, S = (16, 20, 1024) if which == "attn" else (16, 10, 4096)
     q = torch.randn(Bn, S, H * 64, device=dev, dtype=bf)

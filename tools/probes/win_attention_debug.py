@@ -26,16 +26,16 @@ def ref(qkv, rel_h, rel_w, heads):
     return (a @ v).transpose(1, 2).reshape(Bw, Hh, Ww, heads * d)
 
 
-def run(tag, Bw, heads, d, zero_q_tail=False, zero_bias=False):
-    qkv = torch.randn(Bw, 14, 14, 3 * heads * d, device=dev).to(torch.bfloat16)
+def run(tag, Bw, heads, d, zero_q_tail=False, zero_bias=False, Hh=14, Ww=14):
+    qkv = torch.randn(Bw, Hh, Ww, 3 * heads * d, device=dev).to(torch.bfloat16)
     if zero_q_tail:
-        v = qkv.view(Bw, 14, 14, 3, heads, d)
+        v = qkv.view(Bw, Hh, Ww, 3, heads, d)
         v[:, :, :, 0, :, 64:] = 0
-    rh = (torch.randn(27, d, device=dev) * (0 if zero_bias else 1)).to(torch.bfloat16)
-    rw = (torch.randn(27, d, device=dev) * (0 if zero_bias else 1)).to(torch.bfloat16)
+    rh = (torch.randn(2 * Hh - 1, d, device=dev) * (0 if zero_bias else 1)).to(torch.bfloat16)
+    rw = (torch.randn(2 * Ww - 1, d, device=dev) * (0 if zero_bias else 1)).to(torch.bfloat16)
     y = B.sam_attention(qkv, rh, rw, heads).float()
     r = ref(qkv, rh, rw, heads)
-    e = (y - r).abs().reshape(Bw, 196, heads, d)
+    e = (y - r).abs().reshape(Bw, Hh * Ww, heads, d)
     print(f"{tag:34s} max|ref| {r.abs().max():.3f}  err cols[0:64] {e[..., :64].max():.4f}  cols[64:] {e[..., 64:].max():.4f}  "
           f"rows[0:128] {e[:, :128].max():.4f}  rows[128:] {e[:, 128:].max():.4f}  nan {int(torch.isnan(y).sum())}", flush=True)
 
@@ -47,3 +47,7 @@ run("q[64:]=0", 2, 4, 80, zero_q_tail=True)
 run("q[64:]=0, no bias", 2, 4, 80, zero_q_tail=True, zero_bias=True)
 run("d=72", 3, 2, 72)
 run("800 windows-heads", 50, 16, 80)
+run("global 64x64", 1, 2, 80, Hh=64, Ww=64)
+run("global 64x64 no bias", 1, 2, 80, zero_bias=True, Hh=64, Ww=64)
+run("global 8x64 d=72 (2 pairs)", 2, 3, 72, Hh=8, Ww=64)
+run("global 64x64 16 heads", 1, 16, 80, Hh=64, Ww=64)
