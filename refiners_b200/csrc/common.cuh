@@ -156,6 +156,9 @@ struct SdpaProblem {
   // rel_bias_kernel, one [(bias_H + bias_W)][128] block per (b, h, 128-query tile); bias_w is unused (nullptr):
   //   logits[q, kh * bias_W + kw] += blk[kh][q % 128] + blk[bias_H + kw][q % 128]
   const float *bias_h, *bias_w; int bias_H, bias_W;
+  // the relative-position embeddings themselves ([2 H - 1, D], [2 W - 1, D], operand dtype): a kernel that computes the
+  // bias on its own (tc_sdpa_win_fuses_bias) reads these and ignores the table
+  const void *rel_h_emb, *rel_w_emb;
 };
 int simt_sdpa(cudaStream_t st, const SdpaProblem& p);
 bool tc_sdpa_supported(const SdpaProblem& p);
@@ -168,6 +171,7 @@ bool tc_sdpa_short_supported(const SdpaProblem& p);
 int tc_sdpa_short(cudaStream_t st, const SdpaProblem& p);
 // SAM's 14 x 14 windows (tc_attention_win.cu): head dim 65..80, decomposed relative-position bias, 196 queries = keys
 bool tc_sdpa_win_supported(const SdpaProblem& p);
+bool tc_sdpa_win_fuses_bias(const SdpaProblem& p);   // true: the caller need not fill the bias table
 int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p);
 
 }  // namespace rb200

@@ -199,6 +199,23 @@ int sam_attention_impl(cudaStream_t st, int dtype, const void* qkv, const void* 
   const int64_t nq = Bw * heads * HW;
   if (nq > 2147483647LL) RB200_FAIL(-1, "sam_attention: too many queries for one launch");
   float* bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+  const int64_t C = int64_t(heads) * d;
+  const size_t esz = dtype_size(dtype);
+  SdpaProblem p{};
+  p.dtype = dtype;
+  p.q = qkv;
+  p.k = static_cast<const char*>(qkv) + C * esz;
+  p.v = static_cast<const char*>(qkv) + 2 * C * esz;
+  p.o = o;
+  p.B = Bw; p.H = heads; p.Sq = HW; p.Sk = HW; p.D = d;
+  p.q_sb = p.k_sb = p.v_sb = HW * 3 * C;
+  p.q_ss = p.k_ss = p.v_ss = 3 * C;
+  p.o_sb = HW * C; p.o_ss = C;
+  p.scale = 1.0f / sqrtf(float(d));
+  p.bias_h = bias; p.bias_w = nullptr; p.bias_H = Hh; p.bias_W = Ww;  // combined table, see rel_bias_kernel
+  p.rel_h_emb = rel_h_emb; p.rel_w_emb = rel_w_emb;
+  // SAM's 14 x 14 windows: the attention kernel multiplies the queries with the embeddings itself
+  if (kernel_mode() != 1 && tc_sdpa_win_fuses_bias(p)) return tc_sdpa_win(st, p);
   int rc = 0;
   const bool mma = kernel_mode() != 1 && dtype != RB200_FP32 && rel_bias_mma_ok(qkv, rel_h_emb, rel_w_emb, Hh, Ww, d, 2);
   switch (dtype) {
@@ -214,20 +231,6 @@ int sam_attention_impl(cudaStream_t st, int dtype, const void* qkv, const void* 
     default: RB200_FAIL(-1, "sam_attention: bad dtype %d", dtype);
   }
   if (rc) return rc;
-  const int64_t C = int64_t(heads) * d;
-  const size_t esz = dtype_size(dtype);
-  SdpaProblem p{};
-  p.dtype = dtype;
-  p.q = qkv;
-  p.k = static_cast<const char*>(qkv) + C * esz;
-  p.v = static_cast<const char*>(qkv) + 2 * C * esz;
-  p.o = o;
-  p.B = Bw; p.H = heads; p.Sq = HW; p.Sk = HW; p.D = d;
-  p.q_sb = p.k_sb = p.v_sb = HW * 3 * C;
-  p.q_ss = p.k_ss = p.v_ss = 3 * C;
-  p.o_sb = HW * C; p.o_ss = C;
-  p.scale = 1.0f / sqrtf(float(d));
-  p.bias_h = bias; p.bias_w = nullptr; p.bias_H = Hh; p.bias_W = Ww;  // combined table, see rel_bias_kernel
   // tcgen05 path: head dim 80 runs as two 64-column slabs (TMA zero-fills columns 80..127)
   if (kernel_mode() != 1 && tc_sdpa_win_supported(p)) return tc_sdpa_win(st, p);   // the 14 x 14 windows
   if (kernel_mode() != 1 && tc_sdpa_supported(p)) return tc_sdpa(st, p);

@@ -27,6 +27,13 @@
 // 11 bits of a value that is added to logits rounded to bf16 anyway), rel_h[q, kh] is one fp32 scalar per key tile,
 // read from global one tile ahead and folded into the maximum / the exponent offset instead of into every logit.
 //
+// FUSE (GEOM 0): the bias rows are not read from a table that another kernel wrote - they are computed here.  The 27 + 27
+// relative-position embeddings of a layer (the same for every window and head) sit in smem as one more K-major operand
+// [64 rows x 80]; per window and query tile one N = 64 MMA  T = Q R^T  lands in the S buffer ahead of the first logit
+// tile, and each softmax thread scatters its row of T into the [row][30] table: entry idx of a table belongs to the key
+// coordinate  c_q + 13 - idx  (rel_pos[c_q - c_k + 13], image_encoder.py:120-131 of the reference).  That removes the
+// rel_bias kernel (as long as the attention itself at batch 4) and its 45 MB fp32 table round trip per block.
+//
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
 // smem: Q 2 x 20 KB, K/V ring 2 x 40 KB, P 2 x 32 KB, bias 30 KB (34 KB for GEOM 1), 4 KB exchange.
 #include <cuda.h>
@@ -58,13 +65,15 @@ constexpr int P_SLAB = QT * 64 * 2;
 constexpr int P_BYTES = 2 * P_SLAB;
 constexpr int BIAS_PITCH = 30;                     // floats per query row: [0,14) rel_w, [14,28) rel_h, both times log2 e
 constexpr int BIAS_PITCH_G = 136;                  // GEOM 1: bytes per query row, 64 fp16 rel_w entries (+ 8 B: conflict-free LDS.64)
-template <int GEOM> constexpr int bias_bytes() { return GEOM == 0 ? 2 * QT * BIAS_PITCH * 4 : 2 * QT * BIAS_PITCH_G; }
+template <int GEOM> constexpr int bias_bytes() { return GEOM == 0 ? SK * BIAS_PITCH * 4 : 2 * QT * BIAS_PITCH_G; }   // a window has 196 queries
+constexpr int R_SLAB0 = 64 * 128, R_SLAB1 = 64 * 32;   // FUSE: rel_h rows at [0,27), rel_w rows at [32,59) of a 64-row operand
+constexpr int R_BYTES = R_SLAB0 + R_SLAB1;
 constexpr int TMEM_COLS = 512;
 constexpr int XCHG_BYTES = 2 * 2 * 2 * QT * 4;
-template <int GEOM> constexpr size_t smem_bytes() {
-  return Q_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + 1024 + 256 + XCHG_BYTES + bias_bytes<GEOM>();
+template <int GEOM, int FUSE> constexpr size_t smem_bytes() {
+  return Q_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + (FUSE ? R_BYTES : 0) + 1024 + 256 + XCHG_BYTES + bias_bytes<GEOM>();
 }
-static_assert(smem_bytes<0>() <= 227 * 1024 && smem_bytes<1>() <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
+static_assert(smem_bytes<0, 1>() <= 227 * 1024 && smem_bytes<1, 0>() <= 227 * 1024, "exceeds the 227 KB of shared memory a CTA can opt in to");
 constexpr float RESCALE_LOG2 = 8.0f;
 constexpr float L2E = 1.4426950408889634f;
 
@@ -77,7 +86,7 @@ struct WinParams {
   int ntiles;           // 128-key tiles: 2 for a window
   int bias_H;           // rows of the map (GEOM 1)
   float scale_log2e;
-  uint32_t idesc_qk, idesc_pv64, idesc_pv16;
+  uint32_t idesc_qk, idesc_pv64, idesc_pv16, idesc_t;
   int d_out;
   const float* bias;    // [window * H + head][query tile][bias_H rel_h + bias_W rel_w][128] (sam_attention.cu)
 };
@@ -106,6 +115,11 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ uint64_t ld_shared_b64(uint32_t addr) {
   uint64_t v;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));   // volatile: reloaded at every use instead of 14 more live registers
@@ -120,17 +134,21 @@ __device__ __forceinline__ void st_shared_b64(uint32_t addr, float lo, float hi)
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(lo), "f"(hi) : "memory");
 }
 
-template <typename T, int GEOM>
+template <typename T, int GEOM, int FUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                    const __grid_constant__ CUtensorMap map_k0, const __grid_constant__ CUtensorMap map_k1,
-                   const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1, const WinParams p) {
+                   const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_v1,
+                   const __grid_constant__ CUtensorMap map_rh0, const __grid_constant__ CUtensorMap map_rh1,
+                   const __grid_constant__ CUtensorMap map_rw0, const __grid_constant__ CUtensorMap map_rw1, const WinParams p) {
+  static_assert(FUSE == 0 || GEOM == 0, "the fused relative-position product exists for the 14 x 14 windows only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                           // [2 tiles][slab 0 | slab 1]
   uint8_t* sKV = sQ + Q_BYTES;                  // [STAGES][K slab 0 | K slab 1 | V slab 0 | V slab 1]
   uint8_t* sP = sKV + STAGES * STAGE_BYTES;     // [2 groups][2 slabs][128 x 64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  uint8_t* sR = sP + 2 * P_BYTES;               // FUSE: [64 rows][slab 0 | slab 1] relative-position embeddings
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (FUSE ? R_BYTES : 0));
   uint64_t* kv_full = bars;                     // [STAGES]
   uint64_t* kv_empty = bars + STAGES;           // [STAGES]
   uint64_t* q_full = bars + 2 * STAGES;         // [1]
@@ -141,6 +159,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   uint64_t* bar_o = q_full + 8;
   uint64_t* bar_ofree = q_full + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 12);
+  uint64_t* r_full = q_full + 13;               // FUSE: the embeddings have landed
   float* xchg = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
   float* sBias = xchg + XCHG_BYTES / 4;         // [2 groups][128 rows][BIAS_PITCH floats | BIAS_PITCH_G bytes]
 
@@ -160,6 +179,7 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
     }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 2);
+    mbar_init(r_full, 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bar_s[b], 1);
       mbar_init(&bar_sfree[b], 8);
@@ -183,6 +203,14 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         int stage = 0;
         uint32_t phase = 0;
         uint32_t n = 0;
+        if constexpr (FUSE) {
+          const uint32_t r = smem_u32(sR);
+          mbar_arrive_expect_tx(r_full, R_BYTES);   // rows >= 27 of each 32-row box are out of bounds: zero filled, counted
+          tma_load_2d(r, &map_rh0, r_full, 0, 0);
+          tma_load_2d(r + 32 * 128, &map_rw0, r_full, 0, 0);
+          tma_load_2d(r + R_SLAB0, &map_rh1, r_full, 64, 0);
+          tma_load_2d(r + R_SLAB0 + 32 * 32, &map_rw1, r_full, 64, 0);
+        }
         for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
           const int pair = int(w % p.n_pairs);
           const int h = int((w / p.n_pairs) % p.H);
@@ -236,6 +264,18 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
           umma_f16(tmem_s, desc_sw32(qbase + SLAB0), desc_sw32(kb + SLAB0), p.idesc_qk, 1u);  // columns 64..79
           umma_commit(&bar_s[g]);
         };
+        // T_g = Q_g R^T (FUSE): 64 columns of the S buffer, the same hand-over as an S tile
+        auto issue_t = [&]() {
+          if (s_issued > 0) mbar_wait(&bar_sfree[g], (s_issued - 1) & 1, 4);
+          ++s_issued;
+          tcgen05_fence_after();
+          const uint32_t rb = smem_u32(sR);
+          const uint64_t dq = desc_kmajor(qbase), dr = desc_kmajor(rb);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_s, dq + uint64_t(k * 2), dr + uint64_t(k * 2), p.idesc_t, k > 0);
+          umma_f16(tmem_s, desc_sw32(qbase + SLAB0), desc_sw32(rb + R_SLAB0), p.idesc_t, 1u);
+          umma_commit(&bar_s[g]);
+        };
         auto next_k = [&]() {
           if (++st_k == STAGES) {
             st_k = 0;
@@ -244,6 +284,10 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         };
         for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
           mbar_wait(q_full, n & 1, 5);
+          if constexpr (FUSE) {
+            if (n == 0) mbar_wait(r_full, 0, 9);
+            issue_t();
+          }
           mbar_wait(&kv_full[st_k], ph_k, 3);
           issue_s(st_k);
           next_k();
@@ -295,20 +339,22 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
     const uint32_t a_o = smem_u32(&bar_o[g]), a_ofree = smem_u32(&bar_ofree[g]);
     const uint32_t swz = uint32_t(sw) << 4;
     const uint32_t xbar = 1 + g;
-    const uint32_t brow = smem_u32(sBias) + uint32_t(g * QT + row) * (GEOM == 0 ? BIAS_PITCH * 4 : BIAS_PITCH_G);   // this query's bias row
     const bool live = GEOM == 1 || g * QT + row < SK;                       // the query exists
+    // this query's bias row (a window's table has 196 rows: the 60 threads without a query read the last one)
+    const uint32_t brow = smem_u32(sBias) + uint32_t(GEOM == 0 && !live ? SK - 1 : g * QT + row) * (GEOM == 0 ? BIAS_PITCH * 4 : BIAS_PITCH_G);
     T* obase = static_cast<T*>(p.o);
     uint32_t t = 0, n = 0;
+    uint32_t si = 0;                      // tiles taken out of the S buffer so far (FUSE: one more per window than `t`)
     const int nqt = 2 * p.n_pairs, bias_K = GEOM == 0 ? 2 * WIN : p.bias_H + 64;
 
     // GEOM 0: this thread's half of the NEXT window's bias rows (hf 0: the 14 rel_w entries, hf 1: the 14 rel_h entries)
-    float nb[GEOM == 0 ? WIN : 1];
+    float nb[GEOM == 0 && !FUSE ? WIN : 1];
     auto fetch_bias = [&](int64_t w) {
       const float* blk = p.bias + ((w * 2 + g) * (2 * WIN) + (hf == 0 ? WIN : 0)) * 128 + row;
 #pragma unroll
       for (int i = 0; i < WIN; ++i) nb[i] = live ? __ldg(blk + i * 128) : 0.f;
     };
-    if constexpr (GEOM == 0) fetch_bias(blockIdx.x);
+    if constexpr (GEOM == 0 && !FUSE) fetch_bias(blockIdx.x);
 
     for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x, ++n) {
       const int pair = int(w % p.n_pairs);
@@ -318,9 +364,28 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const float* blk = p.bias + (((w / p.n_pairs) * nqt + pair * 2 + g) * bias_K) * 128 + row;
       float bh_cur = 0.f;
       // publish the bias rows (the group's previous reads of the table ended before its last named barrier)
-      if constexpr (GEOM == 0) {
+      if constexpr (GEOM == 0 && FUSE) {
+        // this thread's 32 columns of T = Q R^T: hf 0 the products with rel_h[0..27), hf 1 with rel_w[0..27)
+        mbar_wait_a(a_s, si & 1);
+        ++si;
+        tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + g * 128 + hf * 32 + lane_off, r);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed_a(a_sfree);
+        const int q = g * QT + row, hq = q / WIN;
+        const int c = hf == 0 ? hq : q - hq * WIN;                       // the query's coordinate along this table's axis
+        const uint32_t dst = brow + uint32_t((hf == 0 ? WIN : 0) + c + WIN - 1) * 4;   // entry idx -> key coordinate c + 13 - idx
 #pragma unroll
-        for (int i = 0; i < WIN; i += 2) st_shared_b64(brow + uint32_t((hf == 0 ? 0 : WIN) + i) * 4, nb[i] * L2E, nb[i + 1] * L2E);
+        for (int idx = 0; idx < 2 * WIN - 1; ++idx)
+          if (live && unsigned(c + WIN - 1 - idx) < unsigned(WIN)) st_shared_f32(dst - uint32_t(idx) * 4, __uint_as_float(r[idx]) * L2E);
+      } else if constexpr (GEOM == 0) {
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < WIN; i += 2) st_shared_b64(brow + uint32_t((hf == 0 ? 0 : WIN) + i) * 4, nb[i] * L2E, nb[i + 1] * L2E);
+        }
       } else {
         // rel_w[q, hf * 32 .. + 32) as fp16; rel_h of the first key tile
         const float* bw = blk + (p.bias_H + hf * 32) * 128;
@@ -345,7 +410,8 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         constexpr int K0 = J * KT + HF * 64;                       // GEOM 0: first key of this thread's 64 columns
         constexpr int NV = GEOM == 1 ? 64 : (SK - K0 >= 64 ? 64 : (SK - K0 > 0 ? SK - K0 : 0));   // keys that exist among them (even)
         const bool first = GEOM == 0 ? J == 0 : j == 0;
-        mbar_wait_a(a_s, t & 1);
+        mbar_wait_a(a_s, si & 1);
+        ++si;
         tcgen05_fence_after();
         float s[64];
         {
@@ -476,7 +542,9 @@ tc_sdpa_win_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
           tile(std::integral_constant<int, 1>(), std::integral_constant<int, 1>(), 1);
         }
         // next window's bias rows: in flight while this one is written out
-        if (w + gridDim.x < p.total_work) fetch_bias(w + gridDim.x);
+        if constexpr (!FUSE) {
+          if (w + gridDim.x < p.total_work) fetch_bias(w + gridDim.x);
+        }
       } else {
 #pragma unroll 1
         for (int j = 0; j < p.ntiles; ++j) tile(std::integral_constant<int, -1>(), std::integral_constant<int, -1>(), j);
@@ -579,17 +647,33 @@ bool ok_operand(const void* ptr, int64_t sb, int64_t ss) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ss % 8 == 0 && sb % 8 == 0;
 }
 
-template <typename T, int GEOM>
-int launch(cudaStream_t st, const CUtensorMap (&m)[6], const WinParams& prm) {
+// the relative-position embeddings [2 W - 1, D] as a 2-D map; box = cols x 32 rows
+int make_rel_map(CUtensorMap* map, int dtype, const void* base, int rows, int D, int cols) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) RB200_FAIL(-4, "cuTensorMapEncodeTiled unavailable");
+  const cuuint64_t dims[2] = {cuuint64_t(D), cuuint64_t(rows)};
+  const cuuint64_t strides[1] = {cuuint64_t(D) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(cols), 32};
+  const cuuint32_t es[2] = {1, 1};
+  const CUtensorMapDataType dt = dtype == RB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult rc = fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) RB200_FAIL(-4, "sdpa_win embedding map encode failed (%d): rows=%d D=%d cols=%d", int(rc), rows, D, cols);
+  return 0;
+}
+
+template <typename T, int GEOM, int FUSE>
+int launch(cudaStream_t st, const CUtensorMap (&m)[10], const WinParams& prm) {
   static PerDeviceOnce configured;
   if (configured.needed()) {
-    if (cudaFuncSetAttribute(tc_sdpa_win_kernel<T, GEOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes<GEOM>())) != cudaSuccess)
-      RB200_FAIL(-2, "tc_sdpa_win: cannot reserve %zu bytes of shared memory", smem_bytes<GEOM>());
+    if (cudaFuncSetAttribute(tc_sdpa_win_kernel<T, GEOM, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_bytes<GEOM, FUSE>())) != cudaSuccess)
+      RB200_FAIL(-2, "tc_sdpa_win: cannot reserve %zu bytes of shared memory", smem_bytes<GEOM, FUSE>());
     configured.done();
   }
   const int64_t cap = sm_count();
   const int grid = int(prm.total_work < cap ? prm.total_work : cap);
-  tc_sdpa_win_kernel<T, GEOM><<<grid, NUM_THREADS, smem_bytes<GEOM>(), st>>>(m[0], m[1], m[2], m[3], m[4], m[5], prm);
+  tc_sdpa_win_kernel<T, GEOM, FUSE><<<grid, NUM_THREADS, smem_bytes<GEOM, FUSE>(), st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], prm);
   RB200_CHECK_LAUNCH("tc_sdpa_win");
   return 0;
 }
@@ -622,8 +706,19 @@ bool tc_sdpa_win_supported(const SdpaProblem& p) {
   return ok_operand(p.q, p.q_sb, p.q_ss) && ok_operand(p.k, p.k_sb, p.k_ss) && ok_operand(p.v, p.v_sb, p.v_ss);
 }
 
+// RB200_ATTN_WIN_FUSE: 1 (default) = the kernel computes the windows' relative-position bias itself (the caller then skips
+// the rel_bias kernel), 0 = it reads the table.
+bool tc_sdpa_win_fuses_bias(const SdpaProblem& p) {
+  static const int enabled = [] {
+    const char* e = getenv("RB200_ATTN_WIN_FUSE");
+    return e ? atoi(e) : 1;
+  }();
+  auto al = [](const void* q) { return q != nullptr && (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return enabled && tc_sdpa_win_supported(p) && geometry(p) == 0 && al(p.rel_h_emb) && al(p.rel_w_emb);
+}
+
 int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p) {
-  CUtensorMap m[6];
+  CUtensorMap m[10];
   const void* base[3] = {p.q, p.k, p.v};
   const int64_t sb[3] = {p.q_sb, p.k_sb, p.v_sb}, ss[3] = {p.q_ss, p.k_ss, p.v_ss};
   for (int i = 0; i < 3; ++i) {
@@ -631,6 +726,15 @@ int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p) {
     if (int rc = make_map(&m[2 * i + 1], p.dtype, base[i], p.B, p.Sk, p.H, sb[i], ss[i], p.D, 16)) return rc;
   }
   const int geom = geometry(p);
+  const bool fuse = tc_sdpa_win_fuses_bias(p);
+  if (fuse) {
+    if (int rc = make_rel_map(&m[6], p.dtype, p.rel_h_emb, 2 * WIN - 1, p.D, 64)) return rc;
+    if (int rc = make_rel_map(&m[7], p.dtype, p.rel_h_emb, 2 * WIN - 1, p.D, 16)) return rc;
+    if (int rc = make_rel_map(&m[8], p.dtype, p.rel_w_emb, 2 * WIN - 1, p.D, 64)) return rc;
+    if (int rc = make_rel_map(&m[9], p.dtype, p.rel_w_emb, 2 * WIN - 1, p.D, 16)) return rc;
+  } else {
+    for (int i = 6; i < 10; ++i) m[i] = m[0];   // unused
+  }
   WinParams prm{};
   prm.o = p.o;
   prm.o_sb = p.o_sb;
@@ -646,11 +750,13 @@ int tc_sdpa_win(cudaStream_t st, const SdpaProblem& p) {
   prm.idesc_qk = common | (uint32_t(KT >> 3) << 17);               // D = 128 x 128, A and B K-major
   prm.idesc_pv64 = common | (uint32_t(64 >> 3) << 17) | (1u << 16);   // D = 128 x 64, B (= V) MN-major
   prm.idesc_pv16 = common | (uint32_t(16 >> 3) << 17) | (1u << 16);   // D = 128 x 16
+  prm.idesc_t = common | (uint32_t(64 >> 3) << 17);                   // D = 128 x 64, A and B K-major
   prm.d_out = p.D;
   prm.bias = p.bias_h;
   const bool bf = p.dtype == RB200_BF16;
-  if (geom == 0) return bf ? launch<__nv_bfloat16, 0>(st, m, prm) : launch<__half, 0>(st, m, prm);
-  return bf ? launch<__nv_bfloat16, 1>(st, m, prm) : launch<__half, 1>(st, m, prm);
+  if (geom == 0 && fuse) return bf ? launch<__nv_bfloat16, 0, 1>(st, m, prm) : launch<__half, 0, 1>(st, m, prm);
+  if (geom == 0) return bf ? launch<__nv_bfloat16, 0, 0>(st, m, prm) : launch<__half, 0, 0>(st, m, prm);
+  return bf ? launch<__nv_bfloat16, 1, 0>(st, m, prm) : launch<__half, 1, 0>(st, m, prm);
 }
 
 }  // namespace rb200
