@@ -91,12 +91,6 @@ __device__ __forceinline__ float apply_epilogue(float v, int epi) {
   return v;
 }
 
-__device__ __forceinline__ float apply_epilogue_fast(float v, int epi) {
-  if (epi == RB200_EPI_GELU) return gelu_erf_fast(v);
-  if (epi == RB200_EPI_SILU) return silu_f(v);
-  return v;
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -606,9 +606,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           continue;
         }
-        if (p.epilogue != RB200_EPI_NONE) {
+        // the kind of activation is decided ONCE per 32-column chunk: a per-element switch put a branch between the 32
+        // MUFU chains (ex2, rcp), which then ran one after the other - 444 us instead of 160 us for SAM's 1280 -> 5120
+        // Linear + GeLU at 16384 rows (launch list of config 5), 136 out-of-line division calls in the SASS
+        if (p.epilogue == RB200_EPI_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_epilogue_fast(v[j], p.epilogue);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+        } else if (p.epilogue == RB200_EPI_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu_fast(v[j]);
         }
         T* dst = y + m_lin * p.ldy + n0;
         if (rfast) {
