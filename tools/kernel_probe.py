@@ -34,6 +34,12 @@ elif which == "gemm_geglu":  # Linear 1280 -> 10240 + GLU(GeLU): the largest sin
     x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
     b = torch.randn(N, device=dev, dtype=bf)
     fn, flops = (lambda: B.linear_geglu(x, w, b)), 2.0 * M * N * K
+elif which in ("gemm_mlp", "gemm_mlp_gelu"):  # SAM ViT-H MLP up-projection at batch 4: [16384,1280] x [1280,5120]^T + bias (+ GeLU)
+    M, K, N = 16384, 1280, 5120
+    x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
+    b = torch.randn(N, device=dev, dtype=bf)
+    epi = B.EPI_GELU if which == "gemm_mlp_gelu" else B.EPI_NONE
+    fn, flops = (lambda: B.linear(x, w, b, epilogue=epi)), 2.0 * M * N * K
 elif which == "gemm640":
     M, K, N = 65536, 640, 640
     x, w = torch.randn(M, K, device=dev, dtype=bf), torch.randn(N, K, device=dev, dtype=bf) * 0.03
