@@ -33,27 +33,34 @@ DType = torch.dtype
 NUM_RESIDUALS = 13  # 12 encoder skips + the middle block
 
 
+def _forwarded(name: str) -> property:
+    """A property of the adapter that lives on its control copy (``scale``, ``scale_decay``)."""
+
+    def read(self: "SD1ControlnetAdapter") -> float:
+        return getattr(self.controlnet, name)
+
+    def write(self: "SD1ControlnetAdapter", value: float) -> None:
+        setattr(self.controlnet, name, value)
+
+    return property(read, write)
+
+
 class ConditionEncoder(fl.Chain):
     """``[B, 3, H, W]`` condition image -> ``[B, 320, H/8, W/8]`` (the UNet's first feature map)."""
 
     def __init__(self, device: Device | str | None = None, dtype: DType | None = None) -> None:
         self.out_channels = (16, 32, 96, 256)
-        kw = dict(device=device, dtype=dtype)
-        c = self.out_channels
-        stages = [
-            fl.Chain(
-                fl.Conv2d(c[i], c[i], kernel_size=3, padding=1, **kw),
-                fl.SiLU(),
-                fl.Conv2d(c[i], c[i + 1], kernel_size=3, stride=2, padding=1, **kw),
-                fl.SiLU(),
-            )
-            for i in range(len(c) - 1)
+
+        def conv(cin: int, cout: int, stride: int = 1) -> fl.Conv2d:
+            return fl.Conv2d(cin, cout, kernel_size=3, stride=stride, padding=1, device=device, dtype=dtype)
+
+        widths = self.out_channels
+        stem = fl.Chain(conv(3, widths[0]), fl.SiLU())
+        halvings = [
+            fl.Chain(conv(narrow, narrow), fl.SiLU(), conv(narrow, wide, stride=2), fl.SiLU())
+            for narrow, wide in zip(widths, widths[1:])
         ]
-        super().__init__(
-            fl.Chain(fl.Conv2d(3, c[0], kernel_size=3, stride=1, padding=1, **kw), fl.SiLU()),
-            *stages,
-            fl.Conv2d(c[-1], 320, kernel_size=3, padding=1, **kw),
-        )
+        super().__init__(stem, *halvings, conv(widths[-1], 320))
 
 
 class Controlnet(fl.Passthrough):
@@ -75,36 +82,45 @@ class Controlnet(fl.Passthrough):
         self.scale = scale
         self._scale_decay = scale_decay
         self.compute_scale_decays()
-        kw = dict(device=device, dtype=dtype)
-        temb_key = f"timestep_embedding_{name}"
+        on = dict(device=device, dtype=dtype)
+        self._timestep_key = f"timestep_embedding_{name}"
         super().__init__(
-            TimestepEncoder(context_key=temb_key, **kw),
+            TimestepEncoder(context_key=self._timestep_key, **on),
             fl.Slicing(dim=1, end=4),  # inpainting UNets feed 9 channels; the control copy sees the latents only
-            DownBlocks(in_channels=4, **kw),
-            MiddleBlock(**kw),
+            DownBlocks(in_channels=4, **on),
+            MiddleBlock(**on),
         )
-        # the encoded condition joins right after the input convolution (recomputed every step, like the reference)
-        self.layer(("DownBlocks", 0), fl.Chain).append(
-            fl.Residual(fl.UseContext("controlnet", f"condition_{name}"), ConditionEncoder(**kw))
-        )
+        self._join_condition(on)
+        self._condition_on_timestep(on)
+        self._tap_every_level(on)
+
+    # -- construction steps ------------------------------------------------------------------------------
+    def _join_condition(self, on: dict) -> None:
+        """The encoded condition is added right after the input convolution (recomputed every step, like the reference)."""
+        encoded = fl.Residual(fl.UseContext("controlnet", f"condition_{self.name}"), ConditionEncoder(**on))
+        self.layer(("DownBlocks", 0), fl.Chain).append(encoded)
+
+    def _condition_on_timestep(self, on: dict) -> None:
         for block in self.layers(ResidualBlock):
-            body = block.layer("Chain", fl.Chain)
+            inner = block.layer("Chain", fl.Chain)
             RangeAdapter2d(
-                target=body.layer("Conv2d_1", fl.Conv2d),
-                channels=block.out_channels,
-                embedding_dim=1280,
-                context_key=temb_key,
-                **kw,
-            ).inject(body)
+                target=inner.layer("Conv2d_1", fl.Conv2d), channels=block.out_channels, embedding_dim=1280,
+                context_key=self._timestep_key, **on,
+            ).inject(inner)
+
+    def _tap_every_level(self, on: dict) -> None:
+        """A zero convolution + accumulator at the end of each of the 12 encoder entries and of the middle block."""
+        levels: list[tuple[fl.Chain, int]] = []
         for n, entry in enumerate(self.layer("DownBlocks", DownBlocks)):
             assert isinstance(entry, fl.Chain)
             width = getattr(entry[0], "out_channels", None)
             assert isinstance(width, int), f"first layer of DownBlocks entry {n} does not expose out_channels: {entry[0]}"
-            entry.append(self._tap(width, n, kw))
-        self.layer("MiddleBlock", MiddleBlock).append(self._tap(1280, NUM_RESIDUALS - 1, kw))
-
-    def _tap(self, channels: int, n: int, kw: dict) -> fl.Passthrough:
-        return fl.Passthrough(fl.Conv2d(channels, channels, kernel_size=1, **kw), fl.Lambda(self._accumulate_into(n)))
+            levels.append((entry, width))
+        levels.append((self.layer("MiddleBlock", MiddleBlock), 1280))
+        assert len(levels) == NUM_RESIDUALS
+        for slot, (chain, width) in enumerate(levels):
+            zero_conv = fl.Conv2d(width, width, kernel_size=1, **on)
+            chain.append(fl.Passthrough(zero_conv, fl.Lambda(self._accumulate_into(slot))))
 
     def _accumulate_into(self, n: int):
         def _store_residual(x: Tensor) -> Tensor:  # the name shows in repr(): Lambda(_store_residual(x))
@@ -114,6 +130,7 @@ class Controlnet(fl.Passthrough):
 
         return _store_residual
 
+    # -- the per-level weights -----------------------------------------------------------------------------
     @property
     def scale_decay(self) -> float:
         return self._scale_decay
@@ -125,10 +142,14 @@ class Controlnet(fl.Passthrough):
 
     def compute_scale_decays(self) -> None:
         # 1.0 on the middle block, decaying towards the shallow skips ("prompt is more important" mode at 0.825)
-        self.scale_decays = [self._scale_decay ** float(NUM_RESIDUALS - 1 - i) for i in range(NUM_RESIDUALS)]
+        deepest = NUM_RESIDUALS - 1
+        self.scale_decays = [self._scale_decay ** float(deepest - level) for level in range(NUM_RESIDUALS)]
 
 
 class SD1ControlnetAdapter(fl.Chain, Adapter[SD1UNet]):
+    scale = _forwarded("scale")
+    scale_decay = _forwarded("scale_decay")
+
     def __init__(
         self,
         target: SD1UNet,
@@ -138,10 +159,10 @@ class SD1ControlnetAdapter(fl.Chain, Adapter[SD1UNet]):
         weights: dict[str, Tensor] | None = None,
     ) -> None:
         self.name = name
-        controlnet = Controlnet(name=name, scale=scale, scale_decay=scale_decay, device=target.device, dtype=target.dtype)
+        copy = Controlnet(name=name, scale=scale, scale_decay=scale_decay, device=target.device, dtype=target.dtype)
         if weights is not None:
-            controlnet.load_state_dict(weights)
-        self._controlnet: list[Controlnet] = [controlnet]  # in a list: not a registered sub-module
+            copy.load_state_dict(weights)
+        self._controlnet: list[Controlnet] = [copy]  # in a list: not a registered sub-module
         with self.setup_adapter(target):
             super().__init__(target)
 
@@ -150,9 +171,10 @@ class SD1ControlnetAdapter(fl.Chain, Adapter[SD1UNet]):
         return self._controlnet[0]
 
     def inject(self, parent: fl.Chain | None = None) -> "SD1ControlnetAdapter":
-        present = [layer for layer in self.target if isinstance(layer, Controlnet)]
-        assert self.controlnet not in present, f"{self.controlnet} is already injected"
-        assert all(cn.name != self.name for cn in present), f"Controlnet named {self.name} is already injected"
+        for child in self.target:  # control copies sit at the top level of the UNet, in front of everything else
+            if isinstance(child, Controlnet):
+                assert child is not self.controlnet, f"{self.controlnet} is already injected"
+                assert child.name != self.name, f"Controlnet named {self.name} is already injected"
         self.target.insert(0, self.controlnet)
         return super().inject(parent)
 
@@ -162,22 +184,6 @@ class SD1ControlnetAdapter(fl.Chain, Adapter[SD1UNet]):
 
     def init_context(self) -> Contexts:
         return {"controlnet": {f"condition_{self.name}": None}}
-
-    @property
-    def scale(self) -> float:
-        return self.controlnet.scale
-
-    @scale.setter
-    def scale(self, value: float) -> None:
-        self.controlnet.scale = value
-
-    @property
-    def scale_decay(self) -> float:
-        return self.controlnet.scale_decay
-
-    @scale_decay.setter
-    def scale_decay(self, value: float) -> None:
-        self.controlnet.scale_decay = value
 
     def set_controlnet_condition(self, condition: Tensor) -> None:
         self.set_context("controlnet", {f"condition_{self.name}": condition})
