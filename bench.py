@@ -366,7 +366,7 @@ def workload_name(cfg: int, lb: int) -> str:
 def dominant_kernel_roofline(device: torch.device, peaks: dict, peaks_kind: str, cfg: int, lb: int) -> dict:
     """tc_gemm on the most frequent GEMM of the workload, timed alone with CUDA events, L2 flushed between
     launches.  SDXL: [B*1024, 1280] x [1280, 1280]^T (240 of 743 Linear calls per forward, SURVEY 8a A2);
-    SAM: the MLP up-projection [B*4096, 1280] x [5120, 1280]^T."""
+    SAM: the MLP up-projection [B*4096, 1280] x [5120, 1280]^T with its bias + GeLU epilogue."""
     from refiners_b200 import backend as B
 
     if cfg == 5:
@@ -376,16 +376,21 @@ def dominant_kernel_roofline(device: torch.device, peaks: dict, peaks_kind: str,
     x = torch.randn(M, K, device=device, dtype=torch.bfloat16)
     w = torch.randn(N, K, device=device, dtype=torch.bfloat16) * 0.03
     flush = torch.empty(256 * 1024 * 1024, device=device, dtype=torch.uint8)
+    if cfg == 5:  # as the encoder launches it: bias + GeLU in the epilogue
+        bias = torch.randn(N, device=device, dtype=torch.bfloat16)
+        launch = lambda: B.linear(x, w, bias, epilogue=B.EPI_GELU)  # noqa: E731
+    else:
+        launch = lambda: B.linear(x, w)  # noqa: E731
     with torch.no_grad():
         for _ in range(5):
-            B.linear(x, w)
+            launch()
         torch.cuda.synchronize()
         times = []
         for _ in range(20):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            B.linear(x, w)
+            launch()
             e1.record()
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -406,7 +411,8 @@ def dominant_kernel_roofline(device: torch.device, peaks: dict, peaks_kind: str,
         except Exception:
             pass
     return {
-        "bound": "tensor", "kernel": f"tc_gemm_kernel<bf16, cta_group::2 pair> [{M}x{K}]x[{K}x{N}]^T", "achieved": achieved,
+        "bound": "tensor", "kernel": f"tc_gemm_kernel<bf16, cta_group::2 pair> [{M}x{K}]x[{K}x{N}]^T" + (" + bias + GeLU" if cfg == 5 else ""),
+        "achieved": achieved,
         "peak": peak, "peak_source": f"{peaks_kind} bf16_tflops (burst: kernel timed alone)", "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "ms_per_launch": ms, "ms_per_launch_median": ms_median,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
