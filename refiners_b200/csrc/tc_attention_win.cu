@@ -35,7 +35,7 @@
 // rel_bias kernel (as long as the attention itself at batch 4) and its 45 MB fp32 table round trip per block.
 //
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,336) O_B [384,464).
-// smem: Q 2 x 20 KB, K/V ring 2 x 40 KB, P 2 x 32 KB, bias 30 KB (34 KB for GEOM 1), 4 KB exchange.
+// smem: Q 2 x 20 KB, K/V ring 2 x 40 KB, P 2 x 32 KB, bias table 23 KB (196 rows; GEOM 1: 34 KB), embeddings 10 KB (FUSE), 4 KB exchange.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
