@@ -104,7 +104,13 @@ def save_to_safetensors(path: Path | str, tensors: dict[str, Tensor], metadata: 
 def load_tensors(path: Path | str, /, device: torch.device | str = "cpu") -> dict[str, Tensor]:
     if str(path).endswith(".safetensors"):
         return load_from_safetensors(path, device=device)
-    return torch.load(path, map_location=device, weights_only=True)
+    # a pickle: only plain tensors are unpickled (anything else raises UnpicklingError), and what comes back must be a
+    # flat name -> tensor mapping (contract: the reference's tests/fluxion/test_utils.py:102-125)
+    loaded = torch.load(path, map_location=device, weights_only=True)
+    assert isinstance(loaded, dict), f"{path}: expected a mapping of tensors, found {type(loaded).__name__}"
+    stray = [key for key, value in loaded.items() if not (isinstance(key, str) and isinstance(value, Tensor))]
+    assert not stray, f"{path}: entries that are not str -> Tensor: {stray[:5]}"
+    return loaded
 
 
 # ---------------------------------------------------------------------------- PIL <-> tensors

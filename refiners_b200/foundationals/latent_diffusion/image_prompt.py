@@ -318,6 +318,44 @@ class SDXLIPAdapter(IPAdapter[fl.Chain]):
         )
 
 
+class SD1IPAdapter(IPAdapter[fl.Chain]):
+    """IP-Adapter on an SD 1.5 UNet (contract: stable_diffusion_1/image_prompt.py:9-56 of the reference): four image tokens
+    from the pooled CLIP-H embedding, or ("plus", ``fine_grained``) 16 tokens resampled from its patch features with a
+    768-wide, 12-head PerceiverResampler."""
+
+    def __init__(
+        self,
+        target: fl.Chain,
+        clip_image_encoder: fl.Chain | None = None,
+        image_proj: fl.Module | None = None,
+        scale: float = 1.0,
+        fine_grained: bool = False,
+        weights: dict[str, Tensor] | None = None,
+    ) -> None:
+        if clip_image_encoder is None:
+            from refiners_b200.foundationals.clip.image_encoder import CLIPImageEncoderH
+
+            clip_image_encoder = CLIPImageEncoderH(device=target.device, dtype=target.dtype)
+        if image_proj is not None:
+            assert not fine_grained or isinstance(image_proj, PerceiverResampler)
+        else:
+            text_width = target.ensure_find(CrossAttentionBlock2d).context_embedding_dim
+            on = dict(device=target.device, dtype=target.dtype)
+            if fine_grained:
+                image_proj = PerceiverResampler(
+                    latents_dim=text_width, num_attention_layers=4, num_attention_heads=12, head_dim=64, num_tokens=16,
+                    input_dim=clip_image_encoder.embedding_dim, output_dim=text_width, **on,
+                )
+            else:
+                image_proj = ImageProjection(
+                    clip_image_embedding_dim=clip_image_encoder.output_dim, clip_text_embedding_dim=text_width, **on,
+                )
+        super().__init__(
+            target=target, clip_image_encoder=clip_image_encoder, image_proj=image_proj, scale=scale, fine_grained=fine_grained,
+            weights=weights,
+        )
+
+
 # --------------------------------------------------------------------------- fused execution
 def _fuse_text_image_attention(chain: fl.Sum, inputs: tuple[Any, ...]) -> Any:
     """Sum(SDPA, ImageCrossAttention)(q, k, v) as one dual-KV attention launch."""

@@ -9,9 +9,16 @@ import torch
 from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
+from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
 from refiners_b200.foundationals.latent_diffusion.model import LatentDiffusionModel
 from refiners_b200.foundationals.latent_diffusion.solvers import DDIM, Solver
 from refiners_b200.foundationals.latent_diffusion.stable_diffusion_1.unet import SD1UNet
+
+
+class SD1Autoencoder(LatentDiffusionAutoencoder):
+    """The SD 1.5 VAE: latents = 0.18215 x encoder output (reference stable_diffusion_1/model.py:15-22)."""
+
+    encoder_scale: float = 0.18215
 
 
 class StableDiffusion_1(LatentDiffusionModel):

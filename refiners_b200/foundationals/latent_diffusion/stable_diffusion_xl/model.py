@@ -10,9 +10,16 @@ import torch
 from torch import Tensor
 
 import refiners_b200.fluxion.layers as fl
+from refiners_b200.foundationals.latent_diffusion.auto_encoder import LatentDiffusionAutoencoder
 from refiners_b200.foundationals.latent_diffusion.model import LatentDiffusionModel
 from refiners_b200.foundationals.latent_diffusion.solvers import DDIM, Solver
 from refiners_b200.foundationals.latent_diffusion.stable_diffusion_xl.unet import SDXLUNet
+
+
+class SDXLAutoencoder(LatentDiffusionAutoencoder):
+    """The SDXL VAE: latents = 0.13025 x encoder output (reference stable_diffusion_xl/model.py:12-19)."""
+
+    encoder_scale: float = 0.13025
 
 
 class StableDiffusion_XL(LatentDiffusionModel):
