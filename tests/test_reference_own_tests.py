@@ -35,6 +35,7 @@ FILES = [
     ("tests/adapters/test_t2i_adapter.py", 2),
     ("tests/adapters/test_ip_adapter.py", 4),
     ("tests/foundationals/latent_diffusion/test_sd15_unet.py", 1),
+    ("tests/foundationals/segment_anything/test_utils.py", 5),
 ]
 SLOW = [("tests/adapters/test_controlnet.py", 8)]  # 80 s on 8 cores: RB200_REFERENCE_TESTS=all
 
